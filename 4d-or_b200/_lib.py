@@ -1,0 +1,87 @@
+"""ctypes binding of ``libsg4d.so`` (``include/sg4d.h``).
+
+The library is the product: there is NO fallback.  If the shared object is missing or a call returns
+a non-zero status a ``RuntimeError`` is raised (the reference's launchers print and ``exit(-1)``,
+``_ext-src/include/cuda_utils.h:30-39``; an exception is the Python-visible equivalent of its
+``AT_ASSERT`` host checks, ``_ext-src/include/utils.h:5-25``).
+
+Tensors cross the boundary as raw device pointers (``Tensor.data_ptr()``) plus the current CUDA
+stream handle; no torch types appear in the C signatures.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libsg4d.so")
+
+_i, _i64, _f, _p = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+# name -> argtypes; every function returns an int status.  Kept in the order of include/sg4d.h.
+SIGNATURES = {
+    "sg4d_furthest_point_sampling": [_i, _i, _i, _p, _p, _p, _p],
+    "sg4d_gather_points": [_i, _i, _i, _i, _p, _p, _p, _p],
+    "sg4d_gather_points_grad": [_i, _i, _i, _i, _p, _p, _p, _p],
+    "sg4d_ball_query": [_i, _i, _i, _f, _i, _p, _p, _p, _p],
+    "sg4d_group_points": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
+    "sg4d_group_points_grad": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
+    "sg4d_fps_rows": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "sg4d_ball_query_rows": [_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
+    "sg4d_group_rows": [_i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
+    "sg4d_group_rows_grad": [_i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "sg4d_triplet_gather": [_i64, _i, _i, _p, _p, _p, _p, _p, _p],
+    "sg4d_segment_sum": [_i, _i, _i64, _i, _i, _p, _i, _p, _p, _p, _p],
+}
+OTHER_SYMBOLS = ["sg4d_abi_version", "sg4d_error_string", "sg4d_check_device"]
+
+_lib = None
+
+
+def load():
+    """Load libsg4d.so (once).  Raises if it has not been built -- there is no CPU/PyTorch fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(
+                f"{SO_PATH} is missing: build it with `python 4d-or_b200/build.py` "
+                "(or `python -c 'import __graft_entry__ as g; g.build()'`). sg4d has no fallback path.")
+        lib = ctypes.CDLL(SO_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes, fn.restype = args, _i
+        lib.sg4d_abi_version.restype = _i
+        lib.sg4d_error_string.argtypes, lib.sg4d_error_string.restype = [_i], ctypes.c_char_p
+        lib.sg4d_check_device.restype = _i
+        if lib.sg4d_abi_version() != 1:
+            raise RuntimeError("libsg4d.so ABI version mismatch; rebuild it")
+        _lib = lib
+    return _lib
+
+
+def _check(status, name):
+    if status != 0:
+        msg = load().sg4d_error_string(status).decode()
+        raise RuntimeError(f"{name} failed with status {status}: {msg}")
+
+
+def stream_ptr(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def call(name, ref, *args):
+    """Invoke ``name`` on the current stream of ``ref``'s device."""
+    lib = load()
+    with torch.cuda.device(ref.device):
+        _check(getattr(lib, name)(*args, stream_ptr(ref)), name)
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            # same wording as the reference's host wrappers (sampling.cpp:83, ball_query.cpp:28, ...)
+            raise RuntimeError("CPU not supported")

@@ -1,0 +1,291 @@
+// group.cu -- gather / group kernels for sm_100a.
+//
+// One-to-one replacements of the reference kernels
+//   gather_points(_grad)   EXT/src/sampling_gpu.cu:8-57
+//   group_points(_grad)    EXT/src/group_points_gpu.cu:8-75
+// (channel-major tensors, the operator-API contract) plus the point-major fused variants used by the
+// model path (group + recentre + concat in one pass; deterministic gather-style backward).
+//
+// The reference runs ONE CTA per cloud and lets each thread walk `nsample` outputs (writes strided by
+// nsample*4 B across a warp).  Here every kernel is a flat grid-stride over OUTPUT elements with the
+// fastest-varying output index on threadIdx.x, so stores are fully coalesced and the grid fills all
+// 148 SMs regardless of the number of clouds.
+#include "common.cuh"
+
+namespace sg4d {
+
+// ---------------------------------------------------------------- channel-major (reference layout)
+
+__global__ void __launch_bounds__(256)
+gather_points_kernel(long long total, int c, int n, int m, const float *__restrict__ points,
+                     const int32_t *__restrict__ idx, float *__restrict__ out) {
+    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const int j = (int)(e % m);
+        const long long bc = e / m;  // b*c + l
+        const long long bi = bc / c;
+        out[e] = __ldg(points + bc * n + __ldg(idx + bi * m + j));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gather_points_grad_kernel(long long total, int c, int n, int m, const float *__restrict__ grad_out,
+                          const int32_t *__restrict__ idx, float *__restrict__ grad_points) {
+    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const int j = (int)(e % m);
+        const long long bc = e / m;
+        const long long bi = bc / c;
+        atomicAdd(grad_points + bc * n + __ldg(idx + bi * m + j), __ldg(grad_out + e));
+    }
+}
+
+// out[b,l,j,k] = points[b,l,idx[b,j,k]]; e enumerates (b,l,j,k) with k fastest
+__global__ void __launch_bounds__(256)
+group_points_kernel(long long total, int c, int n, int npoints, int nsample,
+                    const float *__restrict__ points, const int32_t *__restrict__ idx,
+                    float *__restrict__ out) {
+    const long long jk = (long long)npoints * nsample;
+    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const long long bc = e / jk;
+        const long long r = e - bc * jk;  // j*nsample + k
+        const long long bi = bc / c;
+        out[e] = __ldg(points + bc * n + __ldg(idx + bi * jk + r));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+group_points_grad_kernel(long long total, int c, int n, int npoints, int nsample,
+                         const float *__restrict__ grad_out, const int32_t *__restrict__ idx,
+                         float *__restrict__ grad_points) {
+    const long long jk = (long long)npoints * nsample;
+    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const long long bc = e / jk;
+        const long long r = e - bc * jk;
+        const long long bi = bc / c;
+        atomicAdd(grad_points + bc * n + __ldg(idx + bi * jk + r), __ldg(grad_out + e));
+    }
+}
+
+static unsigned flat_grid(long long total) {
+    long long g = (total + 255) / 256;
+    const long long cap = (long long)SG4D_NUM_SMS * 32;  // grid-stride beyond 32 CTAs per SM
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+// ---------------------------------------------------------------- point-major fused grouping
+
+// narrow rows (3 + c <= 16, SA1): one thread per output row, vectorised 16-byte stores
+template <int STRIDE>
+__global__ void __launch_bounds__(256)
+group_rows_narrow_kernel(long long rows, int n, int m, int nsample, int c, int pts_stride,
+                         int feat_stride, int feat_offset, const float *__restrict__ pts,
+                         const float *__restrict__ feats, const float *__restrict__ centers,
+                         const int32_t *__restrict__ idx, float *__restrict__ out) {
+    const long long per_cloud = (long long)m * nsample;
+    for (long long r = blockIdx.x * 256LL + threadIdx.x; r < rows; r += (long long)gridDim.x * 256) {
+        const long long bi = r / per_cloud;
+        const long long j = (r - bi * per_cloud) / nsample;
+        const int i = __ldg(idx + r);
+        const float *p = pts + (bi * n + i) * pts_stride;
+        const float *f = feats + (bi * n + i) * feat_stride + feat_offset;
+        const float *q = centers + (bi * m + j) * 3;
+        float v[STRIDE];
+        v[0] = __ldg(p) - __ldg(q);
+        v[1] = __ldg(p + 1) - __ldg(q + 1);
+        v[2] = __ldg(p + 2) - __ldg(q + 2);
+#pragma unroll
+        for (int ch = 0; ch < STRIDE - 3; ++ch) v[3 + ch] = ch < c ? __ldg(f + ch) : 0.f;
+        float4 *o = reinterpret_cast<float4 *>(out + r * STRIDE);
+#pragma unroll
+        for (int u = 0; u < STRIDE / 4; ++u) o[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+    }
+}
+
+// wide rows (SA2 / anything): one warp per output row, lanes stride over the columns
+__global__ void __launch_bounds__(256)
+group_rows_wide_kernel(long long rows, int n, int m, int nsample, int c, int pts_stride, int feat_stride,
+                       int feat_offset, int out_stride, const float *__restrict__ pts,
+                       const float *__restrict__ feats, const float *__restrict__ centers,
+                       const int32_t *__restrict__ idx, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long per_cloud = (long long)m * nsample;
+    const long long warp0 = (blockIdx.x * 256LL + threadIdx.x) >> 5, nwarp = ((long long)gridDim.x * 256) >> 5;
+    for (long long r = warp0; r < rows; r += nwarp) {
+        const long long bi = r / per_cloud;
+        const long long j = (r - bi * per_cloud) / nsample;
+        const int i = __ldg(idx + r);
+        const float *f = feats + (bi * n + i) * feat_stride + feat_offset;
+        float *o = out + r * out_stride;
+        for (int col = lane; col < out_stride; col += 32) {
+            float v = 0.f;
+            if (col < 3)
+                v = __ldg(pts + (bi * n + i) * pts_stride + col) - __ldg(centers + (bi * m + j) * 3 + col);
+            else if (col < 3 + c)
+                v = __ldg(f + col - 3);
+            o[col] = v;
+        }
+    }
+}
+
+// Backward of the feature columns, as a GATHER (no atomics, fixed summation order).
+// One CTA per (cloud, slice of source points); one warp per source point i; the lanes first search
+// the 128-ish centre rows in parallel (each row of a ball query is an ascending run of `cnt` distinct
+// indices followed by repeats of the first), then walk the hits in (j, k) order while each lane
+// accumulates c/32 channels with coalesced 128-byte reads of grad_out.
+constexpr int kGgWarps = 16;
+__global__ void __launch_bounds__(kGgWarps * 32)
+group_rows_grad_kernel(int n, int m, int nsample, int c, int out_stride, int slices, int accumulate,
+                       const float *__restrict__ grad_out, const int32_t *__restrict__ idx,
+                       const int32_t *__restrict__ cnt, float *__restrict__ grad_feats) {
+    extern __shared__ int32_t s_idx[];  // (m, nsample) indices of this cloud, then (m) counts
+    int32_t *s_cnt = s_idx + (size_t)m * nsample;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cloud = blockIdx.x / slices, slice = blockIdx.x % slices;
+    idx += (size_t)cloud * m * nsample;
+    cnt += (size_t)cloud * m;
+    grad_out += (size_t)cloud * m * nsample * out_stride;
+    grad_feats += (size_t)cloud * n * c;
+    for (int e = tid; e < m * nsample; e += kGgWarps * 32) s_idx[e] = __ldg(idx + e);
+    for (int e = tid; e < m; e += kGgWarps * 32) s_cnt[e] = __ldg(cnt + e);
+    __syncthreads();
+
+    constexpr int kMaxChunk = 8;  // c <= 256
+    const int per_slice = (n + slices - 1) / slices;
+    const int i_end = min(n, (slice + 1) * per_slice);
+    for (int i = slice * per_slice + warp; i < i_end; i += kGgWarps) {
+        float acc[kMaxChunk];
+#pragma unroll
+        for (int u = 0; u < kMaxChunk; ++u) acc[u] = 0.f;
+        for (int j0 = 0; j0 < m; j0 += 32) {
+            const int j = j0 + lane;
+            int pos = -1, cj = 0;
+            if (j < m) {
+                cj = s_cnt[j];
+                if (cj == 0) {  // a row without hits is all zeros: it groups point 0 nsample times
+                    if (i == 0) pos = 0;
+                    cj = 1;
+                } else {
+                    const int32_t *row = s_idx + (size_t)j * nsample;
+                    int lo = 0, hi = cj;  // lower_bound over the ascending prefix [0, cj)
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (row[mid] < i) lo = mid + 1; else hi = mid;
+                    }
+                    if (lo < cj && row[lo] == i) pos = lo;
+                }
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, pos >= 0);
+            while (mask) {
+                const int l = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int jj = j0 + l;
+                const int pp = __shfl_sync(0xffffffffu, pos, l);
+                const int cc = __shfl_sync(0xffffffffu, cj, l);
+                const float *g = grad_out + ((size_t)jj * nsample) * out_stride + 3;
+                // slot pp, then (when i is the first hit) the padding slots cc..nsample-1
+                int k = pp;
+                while (k < nsample) {
+                    const float *gr = g + (size_t)k * out_stride;
+#pragma unroll
+                    for (int u = 0; u < kMaxChunk; ++u) {
+                        const int ch = lane + 32 * u;
+                        if (ch < c) acc[u] += __ldg(gr + ch);
+                    }
+                    if (pp != 0) break;
+                    k = (k == pp) ? cc : k + 1;
+                }
+            }
+        }
+        float *o = grad_feats + (size_t)i * c;
+#pragma unroll
+        for (int u = 0; u < kMaxChunk; ++u) {
+            const int ch = lane + 32 * u;
+            if (ch < c) o[ch] = accumulate ? o[ch] + acc[u] : acc[u];
+        }
+    }
+}
+
+}  // namespace sg4d
+
+using namespace sg4d;
+
+extern "C" int sg4d_gather_points(int b, int c, int n, int npoints, const float *points,
+                                  const int32_t *idx, float *out, sg4d_stream_t stream) {
+    if (b < 0 || c < 0 || n <= 0 || npoints < 0 || !points || !idx || !out) return SG4D_EINVAL;
+    const long long total = (long long)b * c * npoints;
+    if (total == 0) return SG4D_OK;
+    gather_points_kernel<<<flat_grid(total), 256, 0, (cudaStream_t)stream>>>(total, c, n, npoints, points, idx, out);
+    return SG4D_LAUNCH_CHECK();
+}
+
+extern "C" int sg4d_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out,
+                                       const int32_t *idx, float *grad_points, sg4d_stream_t stream) {
+    if (b < 0 || c < 0 || n <= 0 || npoints < 0 || !grad_out || !idx || !grad_points) return SG4D_EINVAL;
+    const long long total = (long long)b * c * npoints;
+    if (total == 0) return SG4D_OK;
+    gather_points_grad_kernel<<<flat_grid(total), 256, 0, (cudaStream_t)stream>>>(total, c, n, npoints, grad_out,
+                                                                                 idx, grad_points);
+    return SG4D_LAUNCH_CHECK();
+}
+
+extern "C" int sg4d_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
+                                 const int32_t *idx, float *out, sg4d_stream_t stream) {
+    if (b < 0 || c < 0 || n <= 0 || npoints < 0 || nsample < 0 || !points || !idx || !out) return SG4D_EINVAL;
+    const long long total = (long long)b * c * npoints * nsample;
+    if (total == 0) return SG4D_OK;
+    group_points_kernel<<<flat_grid(total), 256, 0, (cudaStream_t)stream>>>(total, c, n, npoints, nsample, points,
+                                                                           idx, out);
+    return SG4D_LAUNCH_CHECK();
+}
+
+extern "C" int sg4d_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                                      const int32_t *idx, float *grad_points, sg4d_stream_t stream) {
+    if (b < 0 || c < 0 || n <= 0 || npoints < 0 || nsample < 0 || !grad_out || !idx || !grad_points)
+        return SG4D_EINVAL;
+    const long long total = (long long)b * c * npoints * nsample;
+    if (total == 0) return SG4D_OK;
+    group_points_grad_kernel<<<flat_grid(total), 256, 0, (cudaStream_t)stream>>>(total, c, n, npoints, nsample,
+                                                                                grad_out, idx, grad_points);
+    return SG4D_LAUNCH_CHECK();
+}
+
+extern "C" int sg4d_group_rows(int b, int n, int m, int nsample, int c, int pts_stride, int feat_stride,
+                               int feat_offset, int out_stride, const float *pts, const float *feats,
+                               const float *centers, const int32_t *idx, float *out, sg4d_stream_t stream) {
+    if (b < 0 || n <= 0 || m < 0 || nsample < 0 || c < 0 || pts_stride < 3 || out_stride < 3 + c || !pts ||
+        (!feats && c > 0) || !centers || !idx || !out)
+        return SG4D_EINVAL;
+    const long long rows = (long long)b * m * nsample;
+    if (rows == 0) return SG4D_OK;
+    if (!feats) feats = pts;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_stride == 8 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        group_rows_narrow_kernel<8><<<flat_grid(rows), 256, 0, st>>>(rows, n, m, nsample, c, pts_stride, feat_stride,
+                                                                    feat_offset, pts, feats, centers, idx, out);
+    } else {
+        group_rows_wide_kernel<<<flat_grid(rows * 32), 256, 0, st>>>(rows, n, m, nsample, c, pts_stride, feat_stride,
+                                                                    feat_offset, out_stride, pts, feats, centers,
+                                                                    idx, out);
+    }
+    return SG4D_LAUNCH_CHECK();
+}
+
+extern "C" int sg4d_group_rows_grad(int b, int n, int m, int nsample, int c, int out_stride, int accumulate,
+                                    const float *grad_out, const int32_t *idx, const int32_t *cnt,
+                                    float *grad_feats, sg4d_stream_t stream) {
+    if (b < 0 || n <= 0 || m <= 0 || nsample <= 0 || c <= 0 || c > 256 || out_stride < 3 + c || !grad_out ||
+        !idx || !cnt || !grad_feats)
+        return SG4D_EINVAL;
+    if (b == 0) return SG4D_OK;
+    const size_t smem = ((size_t)m * nsample + m) * sizeof(int32_t);
+    if (smem > 200 * 1024) return SG4D_EINVAL;
+    cudaError_t e = cudaFuncSetAttribute(group_rows_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return status_of(e);
+    // enough CTAs to cover the chip a few times even for a handful of clouds
+    int slices = 1;
+    while ((long long)b * slices < 4LL * SG4D_NUM_SMS && slices * kGgWarps * 2 <= n) slices *= 2;
+    group_rows_grad_kernel<<<(unsigned)(b * slices), kGgWarps * 32, smem, (cudaStream_t)stream>>>(
+        n, m, nsample, c, out_stride, slices, accumulate, grad_out, idx, cnt, grad_feats);
+    return SG4D_LAUNCH_CHECK();
+}

@@ -1,0 +1,63 @@
+"""Scene-sharded data parallelism: one process per GPU, each rank runs the full model on its own
+scenes, and the gradients of the live parameters are summed with ONE all-reduce per step
+(NCCL over NVLink/NVSwitch on the GPU box, gloo in the CPU tests).
+
+The reference has no multi-GPU path (``pl.Trainer(gpus=1)``, SGP/main.py:62); scenes are
+independent units, so this is plain DDP-without-SyncBN semantics (BatchNorm statistics stay
+per-rank).  The never-used ``backbone.fc_layer.*`` parameters (PN2/models/pointnet2_ssg_cls.py:87-96)
+receive no gradient and are left out of the bucket: 3.89 M of the 5.23 M parameters travel.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from torchrun's environment; returns (rank, world, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local_rank
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous block of scenes for ``rank`` (sizes differ by at most one)."""
+    base, rem = divmod(n_items, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+class GradBucket:
+    """Flat fp32 buffer over the gradients of the parameters that actually train."""
+
+    def __init__(self, module, skip_substrings=("backbone.fc_layer.",)):
+        self.params = [p for n, p in module.named_parameters()
+                       if p.requires_grad and not any(s in n for s in skip_substrings)]
+        self.numel = sum(p.numel() for p in self.params)
+        p0 = self.params[0]
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=p0.device)
+        # make every .grad a view into the flat buffer: no pack/unpack copies around the collective
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self):
+        """Sum over ranks then divide by world size (the loss of each rank is a mean over its scenes)."""
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(dist.get_world_size())
+        return self.flat

@@ -1,0 +1,159 @@
+"""Set-abstraction modules with the constructor signatures, attribute names (``npoint``, ``groupers``,
+``mlps``) and ``state_dict`` layout of the reference's ``pointnet2_ops.pointnet2_modules``
+(OPS/pointnet2_modules.py:9-146).
+
+``forward(xyz, features)`` keeps the reference contract (xyz (B,N,3), features (B,C,N) ->
+new_xyz (B,npoint,3), new_features (B,sum C_out,npoint)).  Internally everything runs point-major
+through ``forward_rows``: one FPS launch that also emits the picked centres, one ball-query launch
+for all radii of the level, one fused group+recentre+concat launch per scale, then the shared MLP
+on (rows, channels) matrices and a max over the nsample rows of each centre.  The shared MLP is
+still ``[1x1 conv -> BatchNorm2d -> ReLU] x L`` (modules.py:9-19) evaluated on the same values --
+a 1x1 convolution over (B,C,npoint,nsample) IS a matrix product over rows -- so parameters,
+running statistics and results match the reference module.
+"""
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import rows
+from . import pointnet2_utils
+
+
+def build_shared_mlp(mlp_spec: List[int], bn: bool = True):
+    layers = []
+    for c_in, c_out in zip(mlp_spec[:-1], mlp_spec[1:]):
+        layers.append(nn.Conv2d(c_in, c_out, kernel_size=1, bias=not bn))
+        if bn:
+            layers.append(nn.BatchNorm2d(c_out))
+        layers.append(nn.ReLU(True))
+    return nn.Sequential(*layers)
+
+
+def _batch_norm_rows(bn, x):
+    """nn.BatchNorm2d.forward on a (rows, C) matrix: statistics over rows == over (B, H, W)."""
+    use_batch_stats = bn.training or not bn.track_running_stats
+    momentum = 0.0 if bn.momentum is None else bn.momentum
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if bn.momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    return F.batch_norm(x, bn.running_mean if (not bn.training or bn.track_running_stats) else None,
+                        bn.running_var if (not bn.training or bn.track_running_stats) else None,
+                        bn.weight, bn.bias, use_batch_stats, momentum, bn.eps)
+
+
+def shared_mlp_rows(mlp: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
+    """Apply a ``build_shared_mlp`` stack to x (rows, K_padded); extra zero columns are ignored."""
+    for layer in mlp:
+        if isinstance(layer, nn.Conv2d):
+            w = layer.weight.view(layer.out_channels, layer.in_channels)
+            if x.shape[1] != w.shape[1]:
+                w = F.pad(w, (0, x.shape[1] - w.shape[1]))
+            x = F.linear(x, w, layer.bias)
+        elif isinstance(layer, nn.BatchNorm2d):
+            x = _batch_norm_rows(layer, x)
+        elif isinstance(layer, nn.ReLU):
+            x = F.relu(x, inplace=True)
+        else:
+            raise TypeError(f"unexpected layer in shared MLP: {type(layer).__name__}")
+    return x
+
+
+def _pad4(k):
+    return (k + 3) // 4 * 4
+
+
+class _PointnetSAModuleBase(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.npoint = None
+        self.groupers = None
+        self.mlps = None
+
+    def forward_rows(self, pts: torch.Tensor, feats: Optional[torch.Tensor], feat_offset: int,
+                     c: int) -> Tuple[Optional[torch.Tensor], torch.Tensor]:
+        """Point-major SA level.
+
+        pts (B,n,S): xyz in columns 0..2.  feats (B,n,Sf) or None: the C feature channels are
+        columns feat_offset..feat_offset+c-1 (feats may be the same tensor as pts).
+        Returns (new_xyz (B,npoint,3) or None, new_features (B,npoint,sum C_out) point-major).
+        """
+        b, n = pts.shape[0], pts.shape[1]
+        outs = []
+        if self.npoint is None:  # GroupAll (utils.py:353-383): xyz not recentred, one group of n points
+            cols = [pts[:, :, :3]]
+            if feats is not None and c > 0:
+                cols.append(feats[:, :, feat_offset:feat_offset + c])
+            x = torch.cat(cols, dim=2) if self.groupers[0].use_xyz or feats is None else cols[1]
+            for mlp in self.mlps:
+                y = shared_mlp_rows(mlp, x.reshape(b * n, x.shape[2]))
+                outs.append(y.view(b, n, -1).amax(dim=1, keepdim=True))
+            return None, torch.cat(outs, dim=2) if len(outs) > 1 else outs[0]
+
+        _, new_xyz = rows.fps_rows(pts, self.npoint)
+        radii = [g.radius for g in self.groupers]
+        nsamples = [g.nsample for g in self.groupers]
+        idx, cnt = rows.ball_query_rows(new_xyz, pts, radii, nsamples)
+        for s, mlp in enumerate(self.mlps):
+            assert self.groupers[s].use_xyz, "the hot path always groups xyz (use_xyz=True)"
+            k = 3 + c
+            stride = 8 if k <= 8 else _pad4(k)
+            x = rows.group_rows(pts, feats, new_xyz, idx[s], cnt[s], c, feat_offset, stride)
+            y = shared_mlp_rows(mlp, x.view(-1, stride))
+            outs.append(y.view(b * self.npoint, nsamples[s], -1).amax(dim=1).view(b, self.npoint, -1))
+        return new_xyz, torch.cat(outs, dim=2) if len(outs) > 1 else outs[0]
+
+    def forward(self, xyz: torch.Tensor, features: Optional[torch.Tensor]
+                ) -> Tuple[Optional[torch.Tensor], torch.Tensor]:
+        feats = features.transpose(1, 2).contiguous() if features is not None else None
+        c = feats.shape[2] if feats is not None else 0
+        new_xyz, out = self.forward_rows(xyz.contiguous(), feats, 0, c)
+        return new_xyz, out.transpose(1, 2).contiguous()
+
+
+class PointnetSAModuleMSG(_PointnetSAModuleBase):
+    """Multi-scale-grouping set abstraction (OPS/pointnet2_modules.py:77-115)."""
+
+    def __init__(self, npoint, radii, nsamples, mlps, bn=True, use_xyz=True):
+        super().__init__()
+        assert len(radii) == len(nsamples) == len(mlps)
+        self.npoint = npoint
+        self.groupers = nn.ModuleList()
+        self.mlps = nn.ModuleList()
+        for radius, nsample, spec in zip(radii, nsamples, mlps):
+            self.groupers.append(pointnet2_utils.QueryAndGroup(radius, nsample, use_xyz=use_xyz)
+                                 if npoint is not None else pointnet2_utils.GroupAll(use_xyz))
+            if use_xyz:
+                spec[0] += 3  # in place, like the reference (modules.py:112-113)
+            self.mlps.append(build_shared_mlp(spec, bn))
+
+
+class PointnetSAModule(PointnetSAModuleMSG):
+    """Single-scale set abstraction (OPS/pointnet2_modules.py:118-146)."""
+
+    def __init__(self, mlp, npoint=None, radius=None, nsample=None, bn=True, use_xyz=True):
+        super().__init__(mlps=[mlp], npoint=npoint, radii=[radius], nsamples=[nsample], bn=bn,
+                         use_xyz=use_xyz)
+
+
+class PointnetFPModule(nn.Module):
+    """Feature propagation (OPS/pointnet2_modules.py:149-209).  Constructible for API / state_dict
+    compatibility; its forward needs three_nn / three_interpolate, which are outside the scene-graph
+    hot path."""
+
+    def __init__(self, mlp, bn=True):
+        super().__init__()
+        self.mlp = build_shared_mlp(mlp, bn=bn)
+
+    def forward(self, unknown, known, unknow_feats, known_feats):
+        if known is not None:
+            dist, idx = pointnet2_utils.three_nn(unknown, known)
+            dist_recip = 1.0 / (dist + 1e-8)
+            weight = dist_recip / torch.sum(dist_recip, dim=2, keepdim=True)
+            interpolated = pointnet2_utils.three_interpolate(known_feats, idx, weight)
+        else:
+            interpolated = known_feats.expand(*(list(known_feats.size()[0:2]) + [unknown.size(1)]))
+        x = interpolated if unknow_feats is None else torch.cat([interpolated, unknow_feats], dim=1)
+        return self.mlp(x.unsqueeze(-1)).squeeze(-1)

@@ -1,0 +1,160 @@
+/*
+ * sg4d.h -- C ABI of libsg4d.so, the B200 (sm_100a) implementation of 4D-OR's scene-graph
+ * prediction hot path.
+ *
+ * This is the drop-in boundary.  Every entry point takes raw DEVICE pointers, plain ints/floats and
+ * an explicit cudaStream_t (passed as void*), launches asynchronously on that stream, never
+ * synchronises, keeps no host state and returns an int status (0 = ok, otherwise a cudaError_t
+ * value or one of the SG4D_E* codes below; sg4d_error_string() explains it).  The reference's
+ * launchers instead read the stream from ATen and call exit(-1) on a launch failure
+ * (_ext-src/include/cuda_utils.h:30-39).
+ *
+ * Reference paths are relative to
+ *   scene_graph_prediction/pointnet2_dir/pointnet2_ops_lib/pointnet2_ops/_ext-src/   ("EXT/")
+ *
+ * Section 1 mirrors, one to one, the launcher prototypes the reference's host wrappers bind
+ * (EXT/src/sampling.cpp:4-13, ball_query.cpp:4-6, group_points.cpp:4-10): same argument order and
+ * meaning, same tensor layouts, same zero/1e10 initialisation contract -- plus stream and status.
+ * Section 2 holds the fused entry points the host-side model uses (no reference counterpart as a
+ * single call; each names the reference call sequence it replaces).
+ *
+ * All offsets are 64-bit inside the kernels (the reference's 32-bit ints overflow above 1365 clouds
+ * per call, group_points_gpu.cu:14-16).
+ */
+#ifndef SG4D_H_
+#define SG4D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG4D_ABI_VERSION 1
+
+/* status codes beyond cudaError_t (which occupies small positive ints) */
+#define SG4D_OK 0
+#define SG4D_EINVAL 10001  /* bad shape / null pointer / unsupported size          */
+#define SG4D_ENODEV 10002  /* device is not compute capability 10.x                */
+
+typedef void *sg4d_stream_t; /* a cudaStream_t */
+
+int sg4d_abi_version(void);
+const char *sg4d_error_string(int status);
+/* 0 when the current device can run this library (sm_100), SG4D_ENODEV otherwise */
+int sg4d_check_device(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Section 1 -- one-to-one replacements of the reference launchers
+ * ---------------------------------------------------------------------------------------------- */
+
+/* replaces furthest_point_sampling_kernel_wrapper (EXT/src/sampling.cpp:11-13,
+ * sampling_gpu.cu:175-229).  dataset (b,n,3) fp32; temp (b,n) fp32 scratch -- accepted for ABI
+ * compatibility; the kernel keeps the running minimum distances on chip and only uses temp when a
+ * cloud is too large for that (it then expects it pre-filled with 1e10 like the reference,
+ * sampling.cpp:74-76); may be NULL otherwise.  idxs (b,m) int32.  Bit-identical selection
+ * order to the reference kernel launched with opt_n_threads(n) threads (tie-break included). */
+int sg4d_furthest_point_sampling(int b, int n, int m, const float *dataset, float *temp,
+                                 int32_t *idxs, sg4d_stream_t stream);
+
+/* replaces gather_points_kernel_wrapper (sampling.cpp:4-6, sampling_gpu.cu:8-30).
+ * points (b,c,n) fp32, idx (b,npoints) int32 -> out (b,c,npoints) fp32 */
+int sg4d_gather_points(int b, int c, int n, int npoints, const float *points, const int32_t *idx,
+                       float *out, sg4d_stream_t stream);
+
+/* replaces gather_points_grad_kernel_wrapper (sampling.cpp:7-9, sampling_gpu.cu:34-57).
+ * grad_out (b,c,npoints), idx (b,npoints) -> grad_points (b,c,n), which must be ZERO on entry
+ * (the reference host wrapper allocates it with torch::zeros, sampling.cpp:50-52). */
+int sg4d_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out,
+                            const int32_t *idx, float *grad_points, sg4d_stream_t stream);
+
+/* replaces query_ball_point_kernel_wrapper (ball_query.cpp:4-6, ball_query_gpu.cu:46-54).
+ * new_xyz (b,m,3), xyz (b,n,3) fp32 -> idx (b,m,nsample) int32.  Every slot is written (rows
+ * without any hit are set to 0, which is what the reference's zero-initialised output holds). */
+int sg4d_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                    const float *xyz, int32_t *idx, sg4d_stream_t stream);
+
+/* replaces group_points_kernel_wrapper (group_points.cpp:4-6, group_points_gpu.cu:30-39).
+ * points (b,c,n) fp32, idx (b,npoints,nsample) int32 -> out (b,c,npoints,nsample) fp32 */
+int sg4d_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
+                      const int32_t *idx, float *out, sg4d_stream_t stream);
+
+/* replaces group_points_grad_kernel_wrapper (group_points.cpp:8-10, group_points_gpu.cu:66-75).
+ * grad_out (b,c,npoints,nsample), idx (b,npoints,nsample) -> grad_points (b,c,n), ZERO on entry
+ * (group_points.cpp:49-51). */
+int sg4d_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                           const int32_t *idx, float *grad_points, sg4d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Section 2 -- fused / point-major entry points used by the host-side model
+ *
+ * "Point-major" = one row per point, channels contiguous: a cloud is (n, row_stride) fp32 with
+ * xyz in columns 0..2 of each row and the feature channels after them.  This is the layout the
+ * reference's collate produces before its permute (or_dataset.py:66) and what
+ * PointNetfeat.forward recovers with transpose(1,2) (network_PointNet2.py:23), so no
+ * _break_up_pc / transpose().contiguous() copies are needed (pointnet2_ssg_cls.py:98-102,
+ * pointnet2_modules.py:50-56).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* FPS on strided rows + gather of the picked rows' xyz in one launch.
+ * Replaces furthest_point_sample + gather_operation + 2 transposes (pointnet2_modules.py:50-59).
+ * pts (b,n,row_stride) fp32 with xyz in columns 0..2; idxs (b,m) int32; new_xyz (b,m,3) fp32
+ * (may be NULL).  temp as in sg4d_furthest_point_sampling. */
+int sg4d_fps_rows(int b, int n, int m, int row_stride, const float *pts, float *temp,
+                  int32_t *idxs, float *new_xyz, sg4d_stream_t stream);
+
+/* Ball query for up to SG4D_MAX_SCALES radii over the same centres in ONE scan of the cloud, on
+ * strided rows.  Replaces one ball_query launch per scale (pointnet2_utils.py:318 via
+ * pointnet2_modules.py:61-64).  For scale s: idx[s] (b,m,nsample[s]) int32 and cnt[s] (b,m) int32 =
+ * number of distinct hits found (<= nsample[s]; slots cnt..nsample-1 repeat slot 0, or the whole row
+ * is 0 when cnt == 0).  cnt[s] may be NULL. */
+#define SG4D_MAX_SCALES 4
+int sg4d_ball_query_rows(int b, int n, int m, int row_stride, int center_stride, int nscales,
+                         const float *radius, const int *nsample, const float *centers,
+                         const float *pts, int32_t *const *idx, int32_t *const *cnt,
+                         sg4d_stream_t stream);
+
+/* Grouping into point-major rows, recentring and concatenation fused:
+ *   out[b,j,k, 0:3]  = xyz(pts[b, idx[b,j,k]]) - centers[b,j]            (pointnet2_utils.py:319-321)
+ *   out[b,j,k, 3:3+c] = feats[b, idx[b,j,k], 0:c]                         (pointnet2_utils.py:324-328)
+ * pts (b,n,pts_stride) supplies xyz (columns 0..2); feats (b,n,feat_stride) supplies c channels
+ * starting at column feat_offset (feats may alias pts: SA1 reads rgb/mask from the raw rows).
+ * out (b,m,nsample,out_stride) with out_stride >= 3+c; columns 3+c..out_stride-1 are zeroed.
+ * Replaces 2 x group_points + the in-place subtract + torch.cat. */
+int sg4d_group_rows(int b, int n, int m, int nsample, int c, int pts_stride, int feat_stride,
+                    int feat_offset, int out_stride, const float *pts, const float *feats,
+                    const float *centers, const int32_t *idx, float *out, sg4d_stream_t stream);
+
+/* Backward of the feature part of sg4d_group_rows (replaces group_points_grad,
+ * pointnet2_utils.py:236-241): grad_feats[b,i,0:c] = sum over (j,k) with idx[b,j,k]==i of
+ * grad_out[b,j,k,3:3+c], accumulated in the FIXED order j ascending then k ascending
+ * (deterministic; the reference's atomicAdd order is arbitrary).  Requires every idx row to be the
+ * output of a ball query (ascending distinct hits followed by repeats of the first hit) and cnt
+ * (b,m) from sg4d_ball_query_rows.  grad_feats (b,n,c) is fully overwritten when accumulate == 0
+ * and added to (the second scale of an MSG level) when accumulate != 0. */
+int sg4d_group_rows_grad(int b, int n, int m, int nsample, int c, int out_stride, int accumulate,
+                         const float *grad_out, const int32_t *idx, const int32_t *cnt,
+                         float *grad_feats, sg4d_stream_t stream);
+
+/* TripletGCN message input (network_TripletGCN.py:45-46 + PyG __collect__):
+ *   out[e, 0:d]      = x[dst[e]]      (x_i, edge_index[1])
+ *   out[e, d:d+de]   = edge_feat[e]
+ *   out[e, d+de:2d+de] = x[src[e]]    (x_j, edge_index[0])
+ * x (n_nodes,d), edge_feat (n_edges,de) fp32; src/dst int64 (the reference's edge_index rows). */
+int sg4d_triplet_gather(int64_t n_edges, int d, int de, const float *x, const float *edge_feat,
+                        const int64_t *src, const int64_t *dst, float *out, sg4d_stream_t stream);
+
+/* Deterministic segmented scatter-add (replaces torch_scatter.scatter(reduce='add'),
+ * network_TripletGCN.py:57 and the index_select backward):
+ *   out[v, 0:d] = sum over edges e in order[seg_ptr[v] .. seg_ptr[v+1]) of src[e*src_stride + col0 + 0:d]
+ * and, when src2 != NULL, the same edges' src2[e*src_stride + col1 + 0:d] is added too (the
+ * reference's new_x_i + new_x_j split of the message, network_TripletGCN.py:48-51).
+ * order (n_edges) int32 = edge ids sorted by destination (stable), seg_ptr (n_nodes+1) int32. */
+int sg4d_segment_sum(int n_nodes, int d, int64_t src_stride, int col0, int col1, const float *src,
+                     int has_second, const int32_t *order, const int32_t *seg_ptr, float *out,
+                     sg4d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SG4D_H_ */
