@@ -69,11 +69,41 @@ def stream_ptr(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+LAUNCH_COUNT = 0      # C-ABI calls issued (each launches at least one kernel); read by bench.py
+_TIMING = None        # when a list: (name, first int args, start event, end event) per call
+
+
+def enable_timing(on=True):
+    """Per-call CUDA-event timing on the launching stream (bench.py's roofline numbers)."""
+    global _TIMING
+    _TIMING = [] if on else None
+
+
+def drain_timing():
+    """-> {(name, key): [ms, ...]} for the calls recorded since enable_timing(); synchronises."""
+    global _TIMING
+    rec, _TIMING = _TIMING or [], ([] if _TIMING is not None else None)
+    torch.cuda.synchronize()
+    out = {}
+    for name, key, e0, e1 in rec:
+        out.setdefault((name, key), []).append(e0.elapsed_time(e1))
+    return out
+
+
 def call(name, ref, *args):
     """Invoke ``name`` on the current stream of ``ref``'s device."""
+    global LAUNCH_COUNT
     lib = load()
+    LAUNCH_COUNT += 1
     with torch.cuda.device(ref.device):
-        _check(getattr(lib, name)(*args, stream_ptr(ref)), name)
+        if _TIMING is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _check(getattr(lib, name)(*args, stream_ptr(ref)), name)
+            e1.record()
+            _TIMING.append((name, tuple(a for a in args[:6] if isinstance(a, int) and a < (1 << 31)), e0, e1))
+        else:
+            _check(getattr(lib, name)(*args, stream_ptr(ref)), name)
 
 
 def ptr(t):

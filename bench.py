@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- scenes/s, forward+backward, of the scene-graph hot path on N B200s (BASELINE.json metric).
+
+  python bench.py [--gpus N --steps K --warmup W]            sg4d (this repo) on the GPU(s)
+  python bench.py --impl reference [--gpus N ...]            the reference arithmetic on the host CPU
+
+One "step" = one forward + loss + backward of the full pipeline (both PointNet++ encoders, TripletGCN,
+heads, weighted NLL loss; gradient all-reduce when N > 1) over one batch of synthetic scenes
+(BASELINE configs[2]: 8 scenes x (12 object + 66 edge clouds) x 80 000 points per GPU).  Rank 0 prints
+ONE JSON line; see DESIGN.md "Measurement" for every field.
+
+The reference has no CPU implementation of its custom ops (EXT/src/*.cpp: "CPU not supported"), so the
+reference arm and `cpu_baseline` time the oracle port (oracle/pn2_oracle.c + oracle/model_ref.py: the
+reference's op sequence in stock PyTorch CPU ops) on the box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CLOUDS_PER_SCENE = 78  # 12 objects + 66 edges
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sg4d", choices=["sg4d", "reference"])
+    ap.add_argument("--scenes-per-gpu", type=int, default=8)
+    ap.add_argument("--points", type=int, default=80000, help="points per cloud (BL = 80000)")
+    ap.add_argument("--points-rel", type=int, default=None, help="points per edge cloud (default: --points)")
+    ap.add_argument("--n-obj", type=int, default=12)
+    ap.add_argument("--pairs", default="unordered", choices=["unordered", "ordered"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-clouds", type=int, default=13, help="clouds in the CPU sample (13 = 1/6 scene)")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def model_config():
+    return json.load(open(os.path.join(ROOT, "4d-or_b200", "default_config.json")))
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+
+def cpu_sample_batch(args, n_clouds):
+    """A bounded sample of the workload for the CPU legs: n_clouds clouds of a scene in the scene's own
+    object:edge proportion (12:66), GNN run on as many edges as there are edge clouds."""
+    from sg4d import synthetic
+    n_obj = max(1, round(n_clouds * 12 / CLOUDS_PER_SCENE))
+    n_rel = max(1, n_clouds - n_obj)
+    gen = torch.Generator().manual_seed(4321)
+    pr = args.points_rel or args.points
+    obj = torch.stack([synthetic.make_cloud(gen, args.points, 6) for _ in range(n_obj)])
+    rel = torch.stack([synthetic.make_cloud(gen, pr, 7) for _ in range(n_rel)])
+    ei = torch.stack([torch.randint(0, n_obj, (n_rel,), generator=gen), torch.randint(0, n_obj, (n_rel,), generator=gen)])
+    one_hot = torch.zeros(n_rel, 12)
+    one_hot[:, 0] = 1
+    one_hot[:, 6] = 1
+    return {"obj_points": obj.permute(0, 2, 1), "rel_points": rel.permute(0, 2, 1), "edge_indices": ei,
+            "relation_objects_one_hot": one_hot, "gt_class": torch.randint(0, 12, (n_obj,), generator=gen),
+            "gt_rels": torch.randint(0, 15, (n_rel,), generator=gen)}, n_obj + n_rel
+
+
+def cpu_step(sd, batch):
+    from oracle import model_ref
+    for v in sd.values():
+        if v.requires_grad:
+            v.grad = None
+    outs = model_ref.forward(sd, batch, training=True, dropout=True)
+    loss = model_ref.loss_fn(outs[0], outs[1], batch, torch.ones(12), torch.ones(15), 1e-6)
+    loss.backward()
+    return float(loss)
+
+
+def run_cpu(args, steps, warmup, budget_s):
+    """Times the oracle port on the host cores; returns (scenes/s, ms per step, description dict)."""
+    from oracle import model_ref, pn2_ext_cpu, weights
+    pn2_ext_cpu.build()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    sd = model_ref.clone_state(weights.synth_state_dict(seed=0))
+    n_clouds = args.cpu_clouds
+    while True:
+        batch, used = cpu_sample_batch(args, n_clouds)
+        t0 = time.perf_counter()
+        cpu_step(sd, batch)
+        t1 = time.perf_counter() - t0
+        if t1 * (steps + warmup) <= budget_s or n_clouds <= 2:
+            break
+        n_clouds = max(2, int(n_clouds * budget_s / (t1 * (steps + warmup))))
+    for _ in range(max(0, warmup - 1)):
+        cpu_step(sd, batch)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_step(sd, batch)
+        times.append(time.perf_counter() - t0)
+    per_step = sum(times) / len(times)
+    scenes = used / CLOUDS_PER_SCENE
+    desc = {"kind": "port", "cores": cores, "unit": "scenes/s",
+            "sample": f"{used} of a scene's {CLOUDS_PER_SCENE} clouds ({args.points} pts each), fwd+loss+bwd, "
+                      f"{steps} timed steps of {per_step:.2f} s; oracle/pn2_oracle.c (OpenMP over clouds) + "
+                      f"oracle/model_ref.py (torch CPU, {cores} threads)"}
+    return scenes / per_step, per_step * 1e3, desc
+
+
+def workload_name(args):
+    pr = args.points_rel or args.points
+    n_edge = args.n_obj * (args.n_obj - 1) // (2 if args.pairs == "unordered" else 1)
+    return (f"BASELINE configs[2]: {args.scenes_per_gpu} scenes/GPU x ({args.n_obj} obj x {args.points} pts + "
+            f"{n_edge} edges x {pr} pts), PointNet++ MSG encoders + TripletGCN + heads, fwd+loss+bwd, fp32")
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, ms, desc = run_cpu(args, args.steps, args.warmup, budget_s=200.0)
+    desc["value"] = value
+    line = {"impl": "reference", "metric": "scenes/sec fwd+bwd", "value": value, "unit": "scenes/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "note": "reference has no CPU path for its custom ops; "
+                       "this is the oracle port of its arithmetic on the host cores, rank 0 only"},
+            "cpu_baseline": desc,
+            "e2e": {"value": value, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+
+def main_sg4d(args):
+    import torch.distributed as dist
+    import sg4d
+    from sg4d import _lib, parallel, synthetic
+    from sg4d.model import SGPNModelWrapper
+
+    rank, world, local_rank = parallel.init_from_env()
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl sg4d needs a CUDA device (there is no CPU fallback)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    assert _lib.load().sg4d_check_device() == 0, "sg4d needs an sm_100 (B200) device"
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    cfg = model_config()
+    torch.manual_seed(0)
+    names = [f"rel{i}" for i in range(14)] + ["none"]
+    model = SGPNModelWrapper(cfg, 12, 15, torch.ones(12), torch.ones(15), names).to(dev).train()
+    bucket = parallel.GradBucket(model)
+
+    S = args.scenes_per_gpu
+    pr = args.points_rel or args.points
+    host = synthetic.make_batch(rank * S, S, n_obj=args.n_obj, n_points_obj=args.points, n_points_rel=pr,
+                                pairs=args.pairs)
+    tensor_keys = [k for k, v in host.items() if torch.is_tensor(v)]
+    pinned = {}
+    for k in tensor_keys:
+        v = host[k]
+        if k.endswith("_points"):
+            v = v.permute(0, 2, 1).contiguous().pin_memory().permute(0, 2, 1)
+        else:
+            v = v.contiguous().pin_memory()
+        pinned[k] = v
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
+    resident = synthetic.to_device(pinned, dev)
+
+    def step(batch):
+        bucket.zero()
+        loss = model.training_step(batch)
+        loss.backward()
+        bucket.all_reduce_mean()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(resident)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM (working set of 1.4 GB/step >> 126 MB L2)
+    _lib.enable_timing(True)
+    _lib.drain_timing()
+    launches0 = _lib.LAUNCH_COUNT
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        ev[0].record()
+        for i in range(args.steps):
+            step(resident)
+            ev[i + 1].record()
+        barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    launches = _lib.LAUNCH_COUNT - launches0
+    per_call = _lib.drain_timing()
+    _lib.enable_timing(False)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * S / (ms_per_step / 1e3)
+
+    # ---- timed region 2: end to end through the public API, host (pinned) buffers in, loss out
+    e2e = None
+    if not args.no_e2e:
+        losses = []
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            batch = synthetic.to_device(pinned, dev, non_blocking=True)
+            losses.append(step(batch).detach().to("cpu", non_blocking=False))
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * S / (float(t.item()) / args.steps / 1e3), "unit": "scenes/s",
+               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel table and the roofline of the dominant own kernel
+    peak, peak_src = load_peaks()
+    kernels = []
+    for (name, key), ms in per_call.items():
+        kernels.append({"call": name, "args": list(key), "launches_per_step": len(ms) / args.steps,
+                        "avg_ms": sum(ms) / len(ms), "ms_per_step": sum(ms) / args.steps})
+    kernels.sort(key=lambda k: -k["ms_per_step"])
+    own_ms = sum(k["ms_per_step"] for k in kernels)
+    roof = None
+    for k in kernels:
+        nm, a = k["call"], k["args"]
+        bts = None
+        if nm == "sg4d_fps_rows":
+            bts = a[0] * (4 * a[3] * 0 + 12 * a[1] + 16 * a[2])          # read xyz once, write idx + picked xyz
+        elif nm == "sg4d_group_rows":
+            b_, n_, m_, ns_, c_ = a[:5]
+            bts = b_ * (4 * m_ * ns_ + 4 * (3 + c_) * m_ * ns_ + 12 * m_) + b_ * min(n_, m_ * ns_) * 4 * (3 + c_)
+        elif nm == "sg4d_group_rows_grad":
+            b_, n_, m_, ns_, c_ = a[:5]
+            bts = b_ * (4 * c_ * m_ * ns_ + 4 * m_ * ns_ + 4 * c_ * n_)
+        elif nm == "sg4d_ball_query_rows":
+            b_, n_, m_ = a[:3]
+            bts = b_ * (12 * n_ + 12 * m_)                                # + 4*m*sum(ns) (small)
+        if bts:
+            k["algorithmic_bytes"] = bts
+            k["achieved_gbs"] = bts / (k["avg_ms"] * 1e-3) / 1e9
+            k["hbm_frac"] = k["achieved_gbs"] / peak
+    if kernels:
+        top = next((k for k in kernels if "achieved_gbs" in k), kernels[0])
+        roof = {"bound": "hbm", "kernel": f"{top['call']}{tuple(top['args'])}", "achieved": top.get("achieved_gbs"),
+                "peak": peak, "unit": "GB/s", "frac": top.get("hbm_frac"), "traffic": None, "peak_source": peak_src,
+                "share_of_step": top["ms_per_step"] / ms_per_step}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, _, cpu = run_cpu(args, steps=2, warmup=1, budget_s=45.0)
+        cpu["value"] = v
+
+    line = {"metric": "scenes/sec fwd+bwd", "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "scenes_per_gpu": S, "global_scenes": S * world,
+                       "parallelism": f"dp{world} (scene-sharded, one grad all-reduce)",
+                       "l2": f"inputs are {h2d_bytes / 1e6:.0f} MB per step per GPU (> 126 MB L2), no flush needed"},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
+            "roofline": roof, "cpu_baseline": cpu,
+            "own_kernel_ms_per_step": own_ms, "kernels": kernels[:12]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_sg4d(a)

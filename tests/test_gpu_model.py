@@ -1,0 +1,143 @@
+"""GPU parity tests of the model path (SA module, encoders, TripletGCN, heads, loss, backward) against
+(a) golden fixtures produced by the REFERENCE's own Python and (b) the CPU oracle (oracle/model_ref.py)
+run on the same seeded inputs with the same synthetic state_dict.  Tolerance: 1e-4 absolute on O(1)
+fp32 activations / logits (BASELINE.json north_star), TF32 disabled."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_ref, weights
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = json.load(open(os.path.join(ROOT, "tests", "golden", "no_gt.json")))
+NAMES = [f"r{i}" for i in range(14)] + ["none"]
+
+
+def _model(cuda, sd, lambda_o=0.1, image=False, w_obj=None, w_rel=None):
+    from sg4d.model import SGPNModelWrapper
+    cfg = json.loads(json.dumps(CFG))
+    cfg["MODEL"]["lambda_o"] = lambda_o
+    if image:
+        cfg["IMAGE_INPUT"] = "full"
+    w_obj = torch.ones(12) if w_obj is None else w_obj
+    w_rel = torch.ones(15) if w_rel is None else w_rel
+    m = SGPNModelWrapper(cfg, 12, 15, w_obj, w_rel, NAMES)
+    m.load_state_dict(sd)
+    m.to(cuda).train()
+    m.obj_predictor.dropout.eval()      # train-mode BatchNorm, dropout off
+    m.rel_predictor.dropout.eval()
+    return m
+
+
+def test_sa_module_against_reference_fixture(cuda, golden_dir):
+    from sg4d.pointnet2_ops.pointnet2_modules import PointnetSAModuleMSG
+    fx = np.load(os.path.join(golden_dir, "sa_msg.npz"))
+    shapes = json.loads(str(fx["shapes"]))
+    sa = PointnetSAModuleMSG(npoint=64, radii=[0.25, 0.5], nsamples=[8, 16], mlps=[[5, 16, 24], [5, 16, 32]])
+    sa.load_state_dict(weights.synth_state_dict(shapes, seed=5))
+    sa.to(cuda).train()
+    xyz = torch.from_numpy(fx["xyz"]).to(cuda)
+    feats = torch.from_numpy(fx["feats"]).to(cuda).requires_grad_(True)
+    new_xyz, out = sa(xyz, feats)
+    np.testing.assert_array_equal(new_xyz.cpu().numpy(), fx["new_xyz"])
+    np.testing.assert_allclose(out.detach().cpu().numpy(), fx["out"], rtol=0, atol=1e-4)
+    (out * torch.from_numpy(fx["w"]).to(cuda)).sum().backward()
+    np.testing.assert_allclose(feats.grad.cpu().numpy(), fx["dfeats"], rtol=0, atol=1e-4)
+    params = dict(sa.named_parameters())
+    state = sa.state_dict()
+    for k in fx.files:
+        if k.startswith("grad."):
+            np.testing.assert_allclose(params[k[5:]].grad.cpu().numpy().reshape(fx[k].shape), fx[k], rtol=1e-3,
+                                       atol=1e-4, err_msg=k)
+        if k.startswith("after."):
+            np.testing.assert_allclose(state[k[6:]].cpu().numpy(), fx[k], rtol=1e-5, atol=1e-6, err_msg=k)
+
+
+def test_model_against_reference_fixture(cuda, golden_dir):
+    """BASELINE config 1 shape: 1 scene, 4 objects, 6 edges, 2048 points."""
+    from sg4d import synthetic
+    fx = np.load(os.path.join(golden_dir, "model_cfg1.npz"))
+    sd = weights.synth_state_dict(seed=0)
+    m = _model(cuda, sd, float(fx["lambda_o"]), w_obj=torch.from_numpy(fx["w_obj"]), w_rel=torch.from_numpy(fx["w_rel"]))
+    batch = synthetic.to_device(synthetic.make_scene(0, n_obj=4, n_points_obj=2048, n_points_rel=2048), cuda)
+    outs = m(batch, return_meta_data=True)
+    assert len(outs) == 7 and outs[6] is None
+    for name, t in zip(("obj_cls", "rel_cls", "obj_feature", "rel_feature", "gcn_obj", "gcn_rel"), outs):
+        np.testing.assert_allclose(t.detach().cpu().numpy(), fx[name], rtol=0, atol=1e-4, err_msg=name)
+    loss = m.loss(outs[0], outs[1], batch)
+    np.testing.assert_allclose(loss.item(), float(fx["loss"]), rtol=1e-5)
+    loss.backward()
+    norms = json.loads(str(fx["grad_norms"]))
+    params = dict(m.named_parameters())
+    for k, ref in norms.items():
+        g = params[k].grad
+        if ref is None:
+            assert g is None, k                      # the dead fc_layer parameters
+        else:
+            assert abs(float(g.double().norm()) - ref) <= 2e-4 * max(1.0, ref), (k, float(g.norm()), ref)
+    for k in fx.files:
+        if k.startswith("grad."):
+            np.testing.assert_allclose(params[k[5:]].grad.cpu().numpy(), fx[k], rtol=1e-3, atol=1e-4, err_msg=k)
+        if k.startswith("after."):
+            np.testing.assert_allclose(m.state_dict()[k[6:]].cpu().numpy(), fx[k], rtol=1e-5, atol=1e-6, err_msg=k)
+    m.eval()
+    with torch.no_grad():
+        eo = m(batch)
+    np.testing.assert_allclose(eo[0].cpu().numpy(), fx["eval_obj_cls"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(eo[1].cpu().numpy(), fx["eval_rel_cls"], rtol=0, atol=1e-4)
+
+
+def _oracle_run(sd, batch, lambda_o, image=False):
+    s = model_ref.clone_state(sd)
+    outs = model_ref.forward(s, batch, training=True, dropout=False, image=image)
+    loss = model_ref.loss_fn(outs[0], outs[1], batch, torch.ones(12), torch.ones(15), lambda_o)
+    loss.backward()
+    return s, outs, loss
+
+
+@pytest.mark.parametrize("n_scenes,n_obj,n_pts,pairs,image", [(2, 3, 1500, "ordered", False), (3, 4, 1024, "unordered", True)])
+def test_multi_scene_batch_against_oracle(cuda, n_scenes, n_obj, n_pts, pairs, image):
+    """Concatenated scenes (the batched form the benchmark uses) vs the oracle on the same batch."""
+    from sg4d import synthetic
+    sd = weights.synth_state_dict(seed=1, image=image)
+    batch = synthetic.make_batch(10, n_scenes, n_obj=n_obj, n_points_obj=n_pts, n_points_rel=n_pts + 200, pairs=pairs,
+                                 image=image)
+    s, want, want_loss = _oracle_run(sd, batch, 0.1, image)
+    m = _model(cuda, sd, 0.1, image)
+    db = synthetic.to_device(batch, cuda)
+    outs = m(db, return_meta_data=True)
+    for name, a, b in zip(("obj_cls", "rel_cls", "obj_feature", "rel_feature", "gcn_obj", "gcn_rel"), outs, want):
+        torch.testing.assert_close(a.detach().cpu(), b.detach(), rtol=0, atol=1e-4, msg=lambda s_: name + ": " + s_)
+    loss = m.loss(outs[0], outs[1], db)
+    assert abs(loss.item() - want_loss.item()) <= 1e-5 * max(1.0, abs(want_loss.item()))
+    loss.backward()
+    for k, p in m.named_parameters():
+        g_ref = s[k].grad
+        if g_ref is None:
+            assert p.grad is None, k
+            continue
+        scale = max(1.0, float(g_ref.abs().max()))
+        torch.testing.assert_close(p.grad.cpu(), g_ref, rtol=0, atol=2e-4 * scale, msg=lambda s_: k + ": " + s_)
+    for k, v in m.state_dict().items():              # BatchNorm running statistics after the step
+        if "running" in k and "fc_layer" not in k:
+            torch.testing.assert_close(v.cpu(), s[k], rtol=1e-5, atol=1e-6, msg=lambda s_: k + ": " + s_)
+
+
+def test_ref_shapes_forward_runs(cuda):
+    """Reference run-time shapes (4000 / 8000 points, no_gt.json:40-41), one 9-object scene, ordered pairs."""
+    from sg4d import synthetic
+    sd = weights.synth_state_dict(seed=2)
+    m = _model(cuda, sd, 1e-6)
+    batch = synthetic.to_device(synthetic.make_scene(5, n_obj=9, n_points_obj=4000, n_points_rel=8000, pairs="ordered"), cuda)
+    obj_cls, rel_cls = m(batch)
+    assert obj_cls.shape == (9, 12) and rel_cls.shape == (72, 15)
+    assert torch.isfinite(obj_cls).all() and torch.isfinite(rel_cls).all()
+    torch.testing.assert_close(obj_cls.exp().sum(1), torch.ones(9, device=cuda), rtol=1e-4, atol=1e-4)
+    m.training_step(batch).backward()
+    assert m.obj_encoder.backbone.SA_modules[0].mlps[0][0].weight.grad is not None
+    assert m.obj_encoder.backbone.fc_layer[0].weight.grad is None

@@ -1,0 +1,274 @@
+"""GPU parity tests of the kernels, called through the C ABI (ctypes -> libsg4d.so), against the CPU
+oracle (oracle/pn2_oracle.c) on identical seeded inputs and against the golden fixtures produced by the
+reference's own Python.  Index outputs: bit-exact.  Copies: bit-exact.  Sums: <= 1e-5 absolute (the
+reference's own atomicAdd order is arbitrary)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pn2_ext_cpu as ora
+
+pytestmark = pytest.mark.gpu
+
+
+def _clouds(seed, b, n, kind="mixed"):
+    g = torch.Generator().manual_seed(seed)
+    xyz = torch.rand(b, n, 3, generator=g) * 2 - 1
+    if kind == "mixed":
+        xyz[0, n // 2:] = xyz[0, : n - n // 2]                          # duplicates -> exact FPS ties
+        if b > 1:
+            xyz[1, torch.randperm(n, generator=g)[: max(1, n // 8)]] = 0.0   # zero rows -> skip rule
+            xyz[1, 0] = 0.0
+        if b > 2:
+            xyz[2] = (xyz[2] * 4).round() / 4                           # lattice: many equal distances
+        if b > 3:
+            xyz[3] *= 0.02                                              # almost everything skipped
+    elif kind == "gauss":
+        xyz = torch.randn(b, n, 3, generator=g) * 0.3
+        xyz /= xyz.pow(2).sum(2).sqrt().amax(1, keepdim=True).unsqueeze(-1)
+    return xyz.contiguous()
+
+
+def _ext():
+    from sg4d.pointnet2_ops import _ext
+    return _ext
+
+
+@pytest.mark.parametrize("b,n,m", [(3, 5, 5), (4, 64, 16), (4, 700, 96), (2, 2048, 512), (4, 4000, 512),
+                                   (3, 8000, 512), (2, 13000, 128), (2, 30000, 96), (2, 80000, 512),
+                                   (1, 131072, 64), (1, 200001, 24)])
+def test_fps_bit_exact(cuda, b, n, m):
+    xyz = _clouds(100 + n, b, n)
+    want = ora.furthest_point_sampling(xyz, m)
+    got = _ext().furthest_point_sampling(xyz.to(cuda), m)
+    assert got.dtype == torch.int32 and got.shape == (b, m)
+    np.testing.assert_array_equal(got.cpu().numpy(), want.numpy())
+
+
+def test_fps_all_points_skipped_returns_zeros(cuda):
+    xyz = torch.rand(2, 300, 3) * 0.01          # |p|^2 <= 1e-3 everywhere: the reference emits index 0
+    got = _ext().furthest_point_sampling(xyz.to(cuda), 7).cpu()
+    assert torch.equal(got, ora.furthest_point_sampling(xyz, 7)) and int(got.abs().sum()) == 0
+
+
+@pytest.mark.parametrize("b,n,m,r,ns", [(4, 700, 96, 0.35, 16), (3, 64, 16, 0.5, 8), (2, 2048, 512, 0.1, 16),
+                                        (2, 2048, 512, 0.2, 32), (3, 512, 128, 0.4, 64), (2, 9000, 40, 0.05, 32),
+                                        (1, 80000, 512, 0.1, 16)])
+def test_ball_query_bit_exact(cuda, b, n, m, r, ns):
+    xyz = _clouds(200 + n + ns, b, n, "mixed" if n < 80000 else "gauss")
+    fps = ora.furthest_point_sampling(xyz, m)
+    new_xyz = ora.gather_points(xyz.transpose(1, 2).contiguous(), fps).transpose(1, 2).contiguous()
+    want = ora.ball_query(new_xyz, xyz, r, ns)
+    got = _ext().ball_query(new_xyz.to(cuda), xyz.to(cuda), r, ns)
+    np.testing.assert_array_equal(got.cpu().numpy(), want.numpy())
+
+
+def test_ball_query_rows_without_hits_stay_zero(cuda):
+    xyz = torch.rand(1, 100, 3)
+    far = torch.full((1, 4, 3), 9.0)
+    got = _ext().ball_query(far.to(cuda), xyz.to(cuda), 0.1, 8).cpu()
+    assert int(got.abs().sum()) == 0 and torch.equal(got, ora.ball_query(far, xyz, 0.1, 8))
+
+
+def test_gather_and_group_match_oracle(cuda):
+    g = torch.Generator().manual_seed(5)
+    b, c, n, m, ns = 3, 7, 300, 40, 12
+    pts = torch.randn(b, c, n, generator=g)
+    idx1 = torch.randint(0, n, (b, m), generator=g, dtype=torch.int32)
+    idx2 = torch.randint(0, n, (b, m, ns), generator=g, dtype=torch.int32)
+    e = _ext()
+    assert torch.equal(e.gather_points(pts.to(cuda), idx1.to(cuda)).cpu(), ora.gather_points(pts, idx1))
+    assert torch.equal(e.group_points(pts.to(cuda), idx2.to(cuda)).cpu(), ora.group_points(pts, idx2))
+    go1 = torch.randn(b, c, m, generator=g)
+    go2 = torch.randn(b, c, m, ns, generator=g)
+    torch.testing.assert_close(e.gather_points_grad(go1.to(cuda), idx1.to(cuda), n).cpu(),
+                               ora.gather_points_grad(go1, idx1, n), rtol=0, atol=1e-5)
+    torch.testing.assert_close(e.group_points_grad(go2.to(cuda), idx2.to(cuda), n).cpu(),
+                               ora.group_points_grad(go2, idx2, n), rtol=0, atol=1e-5)
+
+
+def test_operator_api_against_reference_fixture(cuda, golden_dir):
+    """pointnet2_utils (autograd wrappers, QueryAndGroup) vs outputs of the REFERENCE's pointnet2_utils"""
+    from sg4d.pointnet2_ops import pointnet2_utils as U
+    fx = np.load(os.path.join(golden_dir, "ops_small.npz"))
+    for tag in "abc":
+        xyz = torch.from_numpy(fx[f"{tag}_xyz"]).to(cuda)
+        m, r, ns = int(fx[f"{tag}_m"]), float(fx[f"{tag}_r"]), int(fx[f"{tag}_ns"])
+        fps = U.furthest_point_sample(xyz, m)
+        np.testing.assert_array_equal(fps.cpu().numpy(), fx[f"{tag}_fps"])
+        new_xyz = U.gather_operation(xyz.transpose(1, 2).contiguous(), fps).transpose(1, 2).contiguous()
+        np.testing.assert_array_equal(new_xyz.cpu().numpy(), fx[f"{tag}_new_xyz"])
+        np.testing.assert_array_equal(U.ball_query(r, ns, xyz, new_xyz).cpu().numpy(), fx[f"{tag}_ball"])
+        feats = torch.from_numpy(fx[f"{tag}_feats"]).to(cuda).requires_grad_(True)
+        qg = U.QueryAndGroup(r, ns)(xyz, new_xyz, feats)
+        np.testing.assert_array_equal(qg.detach().cpu().numpy(), fx[f"{tag}_qg"])
+        (qg * torch.from_numpy(fx[f"{tag}_w"]).to(cuda)).sum().backward()
+        np.testing.assert_allclose(feats.grad.cpu().numpy(), fx[f"{tag}_dfeats"], rtol=0, atol=1e-5)
+
+
+# ------------------------------------------------------------------ point-major fused operators
+
+@pytest.mark.parametrize("stride,n,m", [(6, 2048, 512), (7, 5000, 128), (3, 512, 128), (7, 80000, 512)])
+def test_fps_rows_equals_fps_on_xyz(cuda, stride, n, m):
+    from sg4d import rows
+    b = 2
+    g = torch.Generator().manual_seed(stride + n)
+    pts = torch.rand(b, n, stride, generator=g)
+    pts[:, :, :3] = _clouds(n + 1, b, n)
+    want = ora.furthest_point_sampling(pts[:, :, :3].contiguous(), m)
+    idx, new_xyz = rows.fps_rows(pts.to(cuda), m)
+    np.testing.assert_array_equal(idx.cpu().numpy(), want.numpy())
+    picked = torch.gather(pts[:, :, :3], 1, want.long().unsqueeze(-1).expand(-1, -1, 3))
+    assert torch.equal(new_xyz.cpu(), picked)
+
+
+@pytest.mark.parametrize("n,m,radii,nss,stride", [(2048, 512, [0.1, 0.2], [16, 32], 6), (512, 128, [0.2, 0.4], [32, 64], 3),
+                                                 (3000, 64, [0.3], [8], 7), (1000, 50, [0.1, 0.2, 0.4], [4, 8, 16], 6)])
+def test_ball_query_rows_multi_radius(cuda, n, m, radii, nss, stride):
+    from sg4d import rows
+    b = 3
+    pts = torch.rand(b, n, stride, generator=torch.Generator().manual_seed(n))
+    pts[:, :, :3] = _clouds(n + 7, b, n)
+    xyz = pts[:, :, :3].contiguous()
+    fps = ora.furthest_point_sampling(xyz, m)
+    new_xyz = ora.gather_points(xyz.transpose(1, 2).contiguous(), fps).transpose(1, 2).contiguous()
+    idx, cnt = rows.ball_query_rows(new_xyz.to(cuda), pts.to(cuda), radii, nss)
+    for s, (r, ns) in enumerate(zip(radii, nss)):
+        want = ora.ball_query(new_xyz, xyz, r, ns)
+        np.testing.assert_array_equal(idx[s].cpu().numpy(), want.numpy())
+        # cnt = number of distinct hits: slots >= cnt repeat slot 0
+        w = want.numpy()
+        d2 = ((new_xyz[:, :, None, :] - xyz[:, None, :, :]) ** 2).sum(-1)
+        assert (cnt[s].cpu().numpy() <= ns).all() and (cnt[s].cpu().numpy() >= 1).all()
+        c = cnt[s].cpu().numpy()
+        for bi in range(b):
+            for j in range(0, m, 7):
+                row = w[bi, j]
+                assert (np.diff(row[: c[bi, j]]) > 0).all() and (row[c[bi, j]:] == row[0]).all()
+        del d2
+
+
+@pytest.mark.parametrize("c,feat_stride,feat_off,n,m,ns", [(3, 6, 3, 2048, 512, 16), (4, 7, 3, 2048, 512, 32),
+                                                           (192, 192, 0, 512, 128, 64), (5, 5, 0, 300, 20, 8)])
+def test_group_rows_forward_backward(cuda, c, feat_stride, feat_off, n, m, ns):
+    from sg4d import rows
+    b = 2
+    g = torch.Generator().manual_seed(c + n)
+    xyz = _clouds(c + n, b, n, "gauss")
+    if feat_off:                                  # SA1 style: features live in the same rows as xyz
+        pts = torch.rand(b, n, feat_stride, generator=g)
+        pts[:, :, :3] = xyz
+        feats = pts
+    else:                                         # SA2 style: separate dense feature rows
+        pts = xyz
+        feats = torch.randn(b, n, feat_stride, generator=g)
+    fps = ora.furthest_point_sampling(xyz, m)
+    new_xyz = ora.gather_points(xyz.transpose(1, 2).contiguous(), fps).transpose(1, 2).contiguous()
+    r = 0.25
+    idx_o = ora.ball_query(new_xyz, xyz, r, ns)
+    idx, cnt = rows.ball_query_rows(new_xyz.to(cuda), pts.to(cuda), [r], [ns])
+    assert torch.equal(idx[0].cpu(), idx_o)
+    stride = 8 if 3 + c <= 8 else (3 + c + 3) // 4 * 4
+    fd = feats.to(cuda).requires_grad_(feat_off == 0)
+    out = rows.group_rows(pts.to(cuda) if feat_off == 0 else fd, fd, new_xyz.to(cuda), idx[0], cnt[0], c, feat_off, stride)
+    # oracle composition in the reference layout
+    gx = ora.group_points(xyz.transpose(1, 2).contiguous(), idx_o) - new_xyz.transpose(1, 2).unsqueeze(-1)
+    fsel = feats[:, :, feat_off:feat_off + c].transpose(1, 2).contiguous()
+    want = torch.cat([gx, ora.group_points(fsel, idx_o)], 1).permute(0, 2, 3, 1)       # (b,m,ns,3+c)
+    got = out.detach().cpu()
+    assert got.shape == (b, m, ns, stride)
+    assert torch.equal(got[..., : 3 + c], want) and float(got[..., 3 + c:].abs().sum()) == 0.0
+    if feat_off == 0:
+        w = torch.randn(b, m, ns, stride, generator=g)
+        (out * w.to(cuda)).sum().backward()
+        want_g = ora.group_points_grad(w[..., 3:3 + c].permute(0, 3, 1, 2).contiguous(), idx_o, n).transpose(1, 2)
+        torch.testing.assert_close(fd.grad.cpu(), want_g, rtol=0, atol=2e-5)
+        # deterministic: a second backward gives the same bits
+        fd.grad = None
+        out2 = rows.group_rows(pts.to(cuda), fd, new_xyz.to(cuda), idx[0], cnt[0], c, feat_off, stride)
+        (out2 * w.to(cuda)).sum().backward()
+        g1 = fd.grad.clone()
+        fd.grad = None
+        out3 = rows.group_rows(pts.to(cuda), fd, new_xyz.to(cuda), idx[0], cnt[0], c, feat_off, stride)
+        (out3 * w.to(cuda)).sum().backward()
+        assert torch.equal(g1, fd.grad)
+
+
+def test_gnn_gather_and_scatter(cuda):
+    from sg4d import rows
+    g = torch.Generator().manual_seed(9)
+    n_nodes, d, de, dh = 24, 256, 256, 512
+    ei = torch.stack([torch.randint(0, n_nodes, (132,), generator=g), torch.randint(0, n_nodes, (132,), generator=g)])
+    x = torch.randn(n_nodes, d, generator=g)
+    e = torch.randn(132, de, generator=g)
+    csr = rows.EdgeCSR(ei.to(cuda), n_nodes)
+    xd, ed = x.to(cuda).requires_grad_(True), e.to(cuda).requires_grad_(True)
+    out = rows.triplet_gather(xd, ed, csr)
+    xr, er = x.clone().requires_grad_(True), e.clone().requires_grad_(True)
+    want = torch.cat([xr.index_select(0, ei[1]), er, xr.index_select(0, ei[0])], 1)
+    assert torch.equal(out.detach().cpu(), want.detach())
+    w = torch.randn(132, 2 * d + de, generator=g)
+    (out * w.to(cuda)).sum().backward()
+    (want * w).sum().backward()
+    torch.testing.assert_close(xd.grad.cpu(), xr.grad, rtol=1e-5, atol=1e-5)
+    assert torch.equal(ed.grad.cpu(), er.grad)
+
+    h = torch.randn(132, 2 * dh + de, generator=g)
+    hd, hr = h.to(cuda).requires_grad_(True), h.clone().requires_grad_(True)
+    m = rows.message_aggregate(hd, dh, de, csr)
+    msg = hr[:, :dh] + hr[:, dh + de:]
+    want_m = torch.zeros(n_nodes, dh).index_add_(0, ei[1], msg)
+    torch.testing.assert_close(m.detach().cpu(), want_m.detach(), rtol=1e-5, atol=1e-5)
+    w2 = torch.randn(n_nodes, dh, generator=g)
+    (m * w2.to(cuda)).sum().backward()
+    (want_m * w2).sum().backward()
+    assert torch.equal(hd.grad.cpu(), hr.grad)
+
+
+# ------------------------------------------------------------------ full-size properties (80 000 points)
+
+def test_full_size_properties(cuda):
+    """BASELINE shapes: size-independent properties instead of a (slow) CPU replay."""
+    from sg4d import rows, synthetic
+    gen = torch.Generator().manual_seed(77)
+    pts = torch.stack([synthetic.make_cloud(gen, 80000, 7) for _ in range(6)]).to(cuda)
+    idx, new_xyz = rows.fps_rows(pts, 512)
+    idx_l = idx.long()
+    xyz = pts[:, :, :3]
+    assert (idx_l[:, 0] == 0).all() and int(idx_l.min()) >= 0 and int(idx_l.max()) < 80000
+    picked = torch.gather(xyz, 1, idx_l.unsqueeze(-1).expand(-1, -1, 3))
+    assert torch.equal(picked, new_xyz)
+    # FPS property: the distance of each pick to the previously picked set never increases
+    for bi in range(pts.shape[0]):
+        d = torch.cdist(picked[bi].double(), picked[bi].double())
+        mins = torch.stack([d[j, :j].min() for j in range(1, 512)])
+        valid = xyz[bi].pow(2).sum(1)[idx_l[bi, 1:]] > 1e-3
+        mv = mins[valid]
+        assert (mv[1:] <= mv[:-1] + 1e-6).all()
+    # repeatable
+    idx2, _ = rows.fps_rows(pts, 512)
+    assert torch.equal(idx, idx2)
+    # ball query: hits inside the radius, ascending, padded with the first hit
+    (i1, i2), (c1, c2) = rows.ball_query_rows(new_xyz, pts, [0.1, 0.2], [16, 32])
+    for ii, cc, r, ns in ((i1, c1, 0.1, 16), (i2, c2, 0.2, 32)):
+        nb = torch.gather(xyz.unsqueeze(1).expand(-1, 512, -1, -1), 2, ii.long().unsqueeze(-1).expand(-1, -1, -1, 3))
+        d2 = (nb - new_xyz.unsqueeze(2)).pow(2).sum(-1)
+        assert float(d2.max()) < r * r * (1 + 1e-5)
+        k = torch.arange(ns, device=cuda)
+        in_prefix = k.view(1, 1, -1) < cc.unsqueeze(-1)
+        asc = (ii[:, :, 1:] > ii[:, :, :-1]) | ~in_prefix[:, :, 1:]
+        assert asc.all() and ((ii == ii[:, :, :1]) | in_prefix).all() and (cc >= 1).all()
+    # one radius answered alone gives the same rows as the fused two-radius pass
+    (j1,), _ = rows.ball_query_rows(new_xyz, pts, [0.1], [16])
+    assert torch.equal(j1, i1)
+
+
+def test_invalid_arguments_raise(cuda):
+    from sg4d import _lib
+    x = torch.zeros(1, 8, 3, device=cuda)
+    with pytest.raises(RuntimeError, match="invalid argument"):
+        _lib.call("sg4d_furthest_point_sampling", x, 1, 0, 4, x.data_ptr(), 0, x.data_ptr())
+    with pytest.raises(RuntimeError, match="invalid argument"):
+        _lib.call("sg4d_ball_query", x, 1, 8, 4, 0.1, 0, x.data_ptr(), x.data_ptr(), x.data_ptr())

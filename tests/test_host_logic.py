@@ -1,0 +1,95 @@
+"""CPU tests of the host-side mirror: state_dict layout, error behaviour, synthetic data, edge CSR."""
+import json
+import os
+
+import pytest
+import torch
+
+import sg4d
+from sg4d import rows, synthetic
+from sg4d.model import SGPNModelWrapper
+from sg4d.pointnet2_ops import _ext, pointnet2_modules, pointnet2_utils
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = json.load(open(os.path.join(ROOT, "tests", "golden", "no_gt.json")))
+
+
+def _model(image=False):
+    cfg = json.loads(json.dumps(CFG))
+    if image:
+        cfg["IMAGE_INPUT"] = "full"
+    return SGPNModelWrapper(cfg, 12, 15, torch.ones(12), torch.ones(15), [f"r{i}" for i in range(14)] + ["none"])
+
+
+def test_state_dict_matches_reference_layout(golden_dir):
+    want = json.load(open(os.path.join(golden_dir, "state_dict_keys.json")))["no_gt"]
+    got = {k: list(v.shape) for k, v in _model().state_dict().items()}
+    assert list(got) == list(want)          # same keys in the same order (188 entries)
+    assert got == want
+    assert sum(p.numel() for p in _model().parameters()) == 5225887
+
+
+def test_image_config_head_width():
+    m = _model(image=True)
+    assert tuple(m.rel_predictor.fc3.weight.shape) == (15, 1036)
+    assert tuple(m.full_image_feature_reduction.weight.shape) == (128, 2048)
+
+
+def test_operator_api_surface():
+    for name in ("furthest_point_sample", "gather_operation", "ball_query", "grouping_operation", "three_nn",
+                 "three_interpolate", "QueryAndGroup", "GroupAll"):
+        assert hasattr(pointnet2_utils, name)
+    for name in ("PointnetSAModuleMSG", "PointnetSAModule", "PointnetFPModule", "build_shared_mlp"):
+        assert hasattr(pointnet2_modules, name)
+    for name in ("gather_points", "gather_points_grad", "furthest_point_sampling", "three_nn", "three_interpolate",
+                 "three_interpolate_grad", "ball_query", "group_points", "group_points_grad"):
+        assert hasattr(_ext, name)     # the nine names of bindings.cpp:6-19
+    spec = [3, 64, 64]
+    pointnet2_modules.PointnetSAModuleMSG(npoint=8, radii=[0.1], nsamples=[4], mlps=[spec])
+    assert spec[0] == 6                # use_xyz bumps the caller's list in place, like the reference
+
+
+def test_cpu_tensors_are_rejected_like_the_reference():
+    xyz = torch.rand(1, 16, 3)
+    with pytest.raises(RuntimeError, match="CPU not supported"):
+        _ext.furthest_point_sampling(xyz, 4)
+    with pytest.raises(RuntimeError, match="CPU not supported"):
+        _ext.ball_query(xyz[:, :4].contiguous(), xyz, 0.1, 4)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        _ext.furthest_point_sampling(torch.rand(1, 3, 16).transpose(1, 2), 4)
+    with pytest.raises(RuntimeError, match="int tensor"):
+        _ext.gather_points(torch.rand(1, 3, 16), torch.zeros(1, 4, dtype=torch.int64))
+    with pytest.raises(NotImplementedError):
+        _ext.three_nn(xyz, xyz)
+
+
+def test_synthetic_scene_contract():
+    sc = synthetic.make_scene(3, n_obj=4, n_points_obj=256, n_points_rel=128)
+    assert sc["obj_points"].shape == (4, 6, 256) and sc["rel_points"].shape == (6, 7, 128)
+    assert sc["obj_points"].transpose(1, 2).is_contiguous()          # collate's permuted view
+    assert sc["edge_indices"].shape == (2, 6) and sc["edge_indices"].dtype == torch.int64
+    assert sc["relation_objects_one_hot"].sum(1).eq(2).all()
+    xyz = sc["obj_points"][:, :3]
+    assert float(xyz.pow(2).sum(1).max()) <= 1.0 + 1e-5
+    assert synthetic.edge_list(12).shape[1] == 66 and synthetic.edge_list(12, "ordered").shape[1] == 132
+    again = synthetic.make_scene(3, n_obj=4, n_points_obj=256, n_points_rel=128)
+    assert torch.equal(sc["rel_points"], again["rel_points"])
+    b = synthetic.make_batch(0, 3, n_obj=4, n_points_obj=64, n_points_rel=64)
+    assert b["obj_points"].shape == (12, 6, 64) and b["rel_points"].shape == (18, 7, 64)
+    assert int(b["edge_indices"].max()) == 11 and b["edge_scene"].tolist() == [0] * 6 + [1] * 6 + [2] * 6
+
+
+def test_edge_csr():
+    ei = torch.tensor([[0, 0, 0, 1, 1, 2, 3], [1, 2, 3, 2, 3, 3, 1]])
+    csr = rows.EdgeCSR(ei, 4)
+    order, ptr = csr.by_dst
+    assert ptr.tolist() == [0, 0, 2, 4, 7]
+    assert order.tolist() == [0, 6, 1, 3, 2, 4, 5]    # stable: ascending edge id within a destination
+    order, ptr = csr.by_src
+    assert ptr.tolist() == [0, 3, 5, 6, 7] and order.tolist() == [0, 1, 2, 3, 4, 5, 6]
+
+
+def test_shard_range():
+    from sg4d import parallel
+    spans = [parallel.shard_range(10, r, 4) for r in range(4)]
+    assert spans == [(0, 3), (3, 6), (6, 8), (8, 10)]
