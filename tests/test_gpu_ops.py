@@ -17,7 +17,7 @@ def _clouds(seed, b, n, kind="mixed"):
     g = torch.Generator().manual_seed(seed)
     xyz = torch.rand(b, n, 3, generator=g) * 2 - 1
     if kind == "mixed":
-        xyz[0, n // 2:] = xyz[0, : n - n // 2]                          # duplicates -> exact FPS ties
+        xyz[0, n // 2:] = xyz[0, : n - n // 2].clone()                          # duplicates -> exact FPS ties
         if b > 1:
             xyz[1, torch.randperm(n, generator=g)[: max(1, n // 8)]] = 0.0   # zero rows -> skip rule
             xyz[1, 0] = 0.0
@@ -105,7 +105,7 @@ def test_operator_api_against_reference_fixture(cuda, golden_dir):
         qg = U.QueryAndGroup(r, ns)(xyz, new_xyz, feats)
         np.testing.assert_array_equal(qg.detach().cpu().numpy(), fx[f"{tag}_qg"])
         (qg * torch.from_numpy(fx[f"{tag}_w"]).to(cuda)).sum().backward()
-        np.testing.assert_allclose(feats.grad.cpu().numpy(), fx[f"{tag}_dfeats"], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(feats.grad.cpu().numpy(), fx[f"{tag}_dfeats"], rtol=1e-5, atol=1e-5)
 
 
 # ------------------------------------------------------------------ point-major fused operators
@@ -140,14 +140,12 @@ def test_ball_query_rows_multi_radius(cuda, n, m, radii, nss, stride):
         np.testing.assert_array_equal(idx[s].cpu().numpy(), want.numpy())
         # cnt = number of distinct hits: slots >= cnt repeat slot 0
         w = want.numpy()
-        d2 = ((new_xyz[:, :, None, :] - xyz[:, None, :, :]) ** 2).sum(-1)
         assert (cnt[s].cpu().numpy() <= ns).all() and (cnt[s].cpu().numpy() >= 1).all()
         c = cnt[s].cpu().numpy()
         for bi in range(b):
             for j in range(0, m, 7):
                 row = w[bi, j]
                 assert (np.diff(row[: c[bi, j]]) > 0).all() and (row[c[bi, j]:] == row[0]).all()
-        del d2
 
 
 @pytest.mark.parametrize("c,feat_stride,feat_off,n,m,ns", [(3, 6, 3, 2048, 512, 16), (4, 7, 3, 2048, 512, 32),

@@ -21,7 +21,7 @@ def ref():
 def _clouds(seed, b, n):
     g = torch.Generator().manual_seed(seed)
     xyz = torch.rand(b, n, 3, generator=g) * 2 - 1
-    xyz[0, n // 2:] = xyz[0, : n - n // 2]
+    xyz[0, n // 2:] = xyz[0, : n - n // 2].clone()
     if b > 1:
         xyz[1, torch.randperm(n, generator=g)[: max(1, n // 8)]] = 0.0
         xyz[1, 0] = 0.0
