@@ -28,12 +28,21 @@ SIGNATURES = {
     "sg4d_group_points_grad": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
     "sg4d_fps_rows": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
     "sg4d_ball_query_rows": [_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
-    "sg4d_group_rows": [_i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
-    "sg4d_group_rows_grad": [_i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "sg4d_group_rows": [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
+    "sg4d_group_rows_grad": [_i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p],
     "sg4d_triplet_gather": [_i64, _i, _i, _p, _p, _p, _p, _p, _p],
     "sg4d_segment_sum": [_i, _i, _i64, _i, _i, _p, _i, _p, _p, _p, _p],
+    "sg4d_pack_weight": [_i, _i, _i, _p, _p, _p],
+    "sg4d_linear_fwd": [_i64, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "sg4d_bn_finalize": [_i, _i, _i64, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p],
+    "sg4d_pool_bwd_da": [_i64, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "sg4d_pool_bwd_dw": [_i64, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "sg4d_inner_bwd_dx": [_i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
+    "sg4d_inner_bwd_dw": [_i64, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "sg4d_partial_sums": [_i, _i, _p, _p, _p],
 }
-OTHER_SYMBOLS = ["sg4d_abi_version", "sg4d_error_string", "sg4d_check_device"]
+OTHER_SYMBOLS = ["sg4d_abi_version", "sg4d_error_string", "sg4d_check_device", "sg4d_mlp_grid",
+                 "sg4d_weight_image_floats", "sg4d_wgrad_partial_floats"]
 
 _lib = None
 
@@ -53,6 +62,9 @@ def load():
         lib.sg4d_abi_version.restype = _i
         lib.sg4d_error_string.argtypes, lib.sg4d_error_string.restype = [_i], ctypes.c_char_p
         lib.sg4d_check_device.restype = _i
+        lib.sg4d_mlp_grid.argtypes, lib.sg4d_mlp_grid.restype = [_i64], _i
+        lib.sg4d_weight_image_floats.argtypes, lib.sg4d_weight_image_floats.restype = [_i, _i], _i64
+        lib.sg4d_wgrad_partial_floats.argtypes, lib.sg4d_wgrad_partial_floats.restype = [_i64, _i], _i64
         if lib.sg4d_abi_version() != 1:
             raise RuntimeError("libsg4d.so ABI version mismatch; rebuild it")
         _lib = lib

@@ -105,7 +105,7 @@ group_rows_narrow_kernel(long long rows, int n, int m, int nsample, int c, int p
 // wide rows (SA2 / anything): one warp per output row, lanes stride over the columns
 __global__ void __launch_bounds__(256)
 group_rows_wide_kernel(long long rows, int n, int m, int nsample, int c, int pts_stride, int feat_stride,
-                       int feat_offset, int out_stride, const float *__restrict__ pts,
+                       int feat_offset, int out_stride, int xyz_col0, const float *__restrict__ pts,
                        const float *__restrict__ feats, const float *__restrict__ centers,
                        const int32_t *__restrict__ idx, float *__restrict__ out) {
     const int lane = threadIdx.x & 31;
@@ -117,12 +117,13 @@ group_rows_wide_kernel(long long rows, int n, int m, int nsample, int c, int pts
         const int i = __ldg(idx + r);
         const float *f = feats + (bi * n + i) * feat_stride + feat_offset;
         float *o = out + r * out_stride;
+        const int fcol0 = xyz_col0 == 0 ? 3 : 0;   // features first (xyz_col0 == c) or xyz first (xyz_col0 == 0)
         for (int col = lane; col < out_stride; col += 32) {
             float v = 0.f;
-            if (col < 3)
-                v = __ldg(pts + (bi * n + i) * pts_stride + col) - __ldg(centers + (bi * m + j) * 3 + col);
-            else if (col < 3 + c)
-                v = __ldg(f + col - 3);
+            if (col >= xyz_col0 && col < xyz_col0 + 3)
+                v = __ldg(pts + (bi * n + i) * pts_stride + (col - xyz_col0)) - __ldg(centers + (bi * m + j) * 3 + (col - xyz_col0));
+            else if (col >= fcol0 && col < fcol0 + c)
+                v = __ldg(f + col - fcol0);
             o[col] = v;
         }
     }
@@ -135,7 +136,7 @@ group_rows_wide_kernel(long long rows, int n, int m, int nsample, int c, int pts
 // accumulates c/32 channels with coalesced 128-byte reads of grad_out.
 constexpr int kGgWarps = 16;
 __global__ void __launch_bounds__(kGgWarps * 32)
-group_rows_grad_kernel(int n, int m, int nsample, int c, int out_stride, int slices, int accumulate,
+group_rows_grad_kernel(int n, int m, int nsample, int c, int out_stride, int gcol0, int slices, int accumulate,
                        const float *__restrict__ grad_out, const int32_t *__restrict__ idx,
                        const int32_t *__restrict__ cnt, float *__restrict__ grad_feats) {
     extern __shared__ int32_t s_idx[];  // (m, nsample) indices of this cloud, then (m) counts
@@ -182,7 +183,7 @@ group_rows_grad_kernel(int n, int m, int nsample, int c, int out_stride, int sli
                 const int jj = j0 + l;
                 const int pp = __shfl_sync(0xffffffffu, pos, l);
                 const int cc = __shfl_sync(0xffffffffu, cj, l);
-                const float *g = grad_out + ((size_t)jj * nsample) * out_stride + 3;
+                const float *g = grad_out + ((size_t)jj * nsample) * out_stride + gcol0;
                 // slot pp, then (when i is the first hit) the padding slots cc..nsample-1
                 int k = pp;
                 while (k < nsample) {
@@ -251,30 +252,31 @@ extern "C" int sg4d_group_points_grad(int b, int c, int n, int npoints, int nsam
 }
 
 extern "C" int sg4d_group_rows(int b, int n, int m, int nsample, int c, int pts_stride, int feat_stride,
-                               int feat_offset, int out_stride, const float *pts, const float *feats,
+                               int feat_offset, int out_stride, int xyz_col0, const float *pts, const float *feats,
                                const float *centers, const int32_t *idx, float *out, sg4d_stream_t stream) {
     if (b < 0 || n <= 0 || m < 0 || nsample < 0 || c < 0 || pts_stride < 3 || out_stride < 3 + c || !pts ||
+        (xyz_col0 != 0 && xyz_col0 != c) ||
         (!feats && c > 0) || !centers || !idx || !out)
         return SG4D_EINVAL;
     const long long rows = (long long)b * m * nsample;
     if (rows == 0) return SG4D_OK;
     if (!feats) feats = pts;
     cudaStream_t st = (cudaStream_t)stream;
-    if (out_stride == 8 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    if (out_stride == 8 && xyz_col0 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
         group_rows_narrow_kernel<8><<<flat_grid(rows), 256, 0, st>>>(rows, n, m, nsample, c, pts_stride, feat_stride,
                                                                     feat_offset, pts, feats, centers, idx, out);
     } else {
         group_rows_wide_kernel<<<flat_grid(rows * 32), 256, 0, st>>>(rows, n, m, nsample, c, pts_stride, feat_stride,
-                                                                    feat_offset, out_stride, pts, feats, centers,
-                                                                    idx, out);
+                                                                    feat_offset, out_stride, xyz_col0, pts, feats,
+                                                                    centers, idx, out);
     }
     return SG4D_LAUNCH_CHECK();
 }
 
-extern "C" int sg4d_group_rows_grad(int b, int n, int m, int nsample, int c, int out_stride, int accumulate,
+extern "C" int sg4d_group_rows_grad(int b, int n, int m, int nsample, int c, int out_stride, int gcol0, int accumulate,
                                     const float *grad_out, const int32_t *idx, const int32_t *cnt,
                                     float *grad_feats, sg4d_stream_t stream) {
-    if (b < 0 || n <= 0 || m <= 0 || nsample <= 0 || c <= 0 || c > 256 || out_stride < 3 + c || !grad_out ||
+    if (b < 0 || n <= 0 || m <= 0 || nsample <= 0 || c <= 0 || c > 256 || gcol0 < 0 || out_stride < gcol0 + c || !grad_out ||
         !idx || !cnt || !grad_feats)
         return SG4D_EINVAL;
     if (b == 0) return SG4D_OK;
@@ -286,6 +288,6 @@ extern "C" int sg4d_group_rows_grad(int b, int n, int m, int nsample, int c, int
     int slices = 1;
     while ((long long)b * slices < 4LL * SG4D_NUM_SMS && slices * kGgWarps * 2 <= n) slices *= 2;
     group_rows_grad_kernel<<<(unsigned)(b * slices), kGgWarps * 32, smem, (cudaStream_t)stream>>>(
-        n, m, nsample, c, out_stride, slices, accumulate, grad_out, idx, cnt, grad_feats);
+        n, m, nsample, c, out_stride, gcol0, slices, accumulate, grad_out, idx, cnt, grad_feats);
     return SG4D_LAUNCH_CHECK();
 }

@@ -1,0 +1,846 @@
+// mlp.cu -- the shared point-MLP of a set-abstraction level on the 5th-generation tensor cores.
+//
+// Replaces, for one scale of build_shared_mlp (OPS/pointnet2_modules.py:9-19,66-70), the chain
+//     [Conv2d(1x1, bias=False) -> BatchNorm2d (batch statistics) -> ReLU(inplace)] x 2 -> max_pool2d over nsample
+// forward AND backward, which the reference runs as separate cuDNN / ATen launches with
+// (B,C,npoint,nsample) activations round-tripping HBM between every op.
+//
+// A 1x1 convolution over (B,C,npoint,nsample) is Y[R,N] = A[R,K] * W[N,K]^T over the R = B*npoint*nsample rows
+// of the point-major grouped tensor.  Two persistent, warp-specialised kernel families share one engine:
+//
+//   row_gemm_kernel  (T1)   D[128-row tile, N] = P(tile)[128, K] * W^T      forward layers, dA and dX
+//   wgrad_kernel     (T2)   D[M, N] += P(tile)^T[M, 128] * Q(tile)[128, N]  weight gradients, K = rows
+//
+//   producers (4 warps)  build the operand tiles: coalesced 16-byte loads from HBM, an elementwise PROLOGUE
+//                        applied in registers (BatchNorm scale/shift + ReLU of the previous layer in the forward
+//                        pass; the BatchNorm / ReLU / max-pool backward formulas in the backward pass -- so
+//                        neither normalised activations nor dY tensors ever exist in memory), a round-to-nearest
+//                        split into TF32 hi + lo parts, and stores into 128-byte-swizzled shared-memory tiles.
+//                        Weight k-blocks (pre-split, pre-swizzled image) arrive by one bulk-TMA copy per stage.
+//   MMA (1 thread)       tcgen05.mma kind::tf32, three products per k-step (lo*hi + hi*lo + hi*hi: "3xTF32",
+//                        fp32-level accuracy; plain TF32 would miss the 1e-4 parity bound), fp32 accumulators in
+//                        TMEM (double buffered across tiles in T1, resident for the whole kernel in T2).
+//   epilogue (4 warps)   tcgen05.ld the accumulator, stage it in shared memory, store coalesced, and in the same
+//                        pass produce the per-channel reductions BatchNorm needs (fp64 across tiles) and, for the
+//                        last layer of a scale, the per-group (nsample rows) max or min pre-activation and its
+//                        row.  BatchNorm+ReLU are monotone per channel, so max_k relu(bn(y_k)) = relu(bn(max_k y_k))
+//                        for a non-negative scale and relu(bn(min_k y_k)) otherwise.
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace sg4d {
+
+constexpr int kTileM = 128;       // rows per tile = UMMA M
+constexpr int kKB = 32;           // fp32 per k-block (one 128-byte swizzle row)
+constexpr int kStages = 2;
+constexpr int kProdThreads = 256, kEpiThreads = 128;
+constexpr int kProdWarps = kProdThreads / 32;
+constexpr int kProdRows = kTileM * 8 / kProdThreads;          // float4 items per producer thread per T1 k-block
+constexpr int kMlpThreads = kProdThreads + 32 + kEpiThreads;   // warps 0-7 producers, 8 MMA, 9-12 epilogue
+
+// ------------------------------------------------------------------------------------------------
+// Operand generator: element (row, col) of the logical operand matrix P, computed from arrays in HBM.
+//   mode 0   P = A
+//   mode 1   P = relu(A * s + t)                              BatchNorm + ReLU of the previous layer
+//   mode 2   P = dsel[g] * [row % S == garg[g]] - (A * s + t)  dY of a pooled layer (A = Y; g = row / S)
+//   mode 3   P = A2 * p - (A * s + t)                          dY of an inner layer (A = Y, A2 = dZ)
+struct Operand {
+    const float *A;
+    int lda;
+    const float *A2;
+    int lda2;
+    const float *s, *t, *p;     // per-column constants (length >= ncols)
+    const float *dsel;          // (rows / S, ldsel)
+    const uint8_t *garg;
+    int S, logS, ldsel;         // S = 1 << logS rows per group
+    int ncols;                  // valid columns; beyond -> 0
+};
+
+struct RawVec {                 // what one thread fetches for 4 consecutive columns of one row
+    float4 a, a2;
+    uint32_t arg;
+};
+
+template <int MODE>
+__device__ __forceinline__ void op_load(const Operand &o, long long row, long long nrows, int col, RawVec &r) {
+    const bool ok = row < nrows && col < o.ncols;
+    r.a = ok ? __ldg(reinterpret_cast<const float4 *>(o.A + row * o.lda + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODE == 3)
+        r.a2 = ok ? __ldg(reinterpret_cast<const float4 *>(o.A2 + row * o.lda2 + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODE == 2) {
+        const long long g = row >> o.logS;
+        r.a2 = ok ? __ldg(reinterpret_cast<const float4 *>(o.dsel + g * o.ldsel + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        r.arg = ok ? __ldg(reinterpret_cast<const uint32_t *>(o.garg + g * o.ldsel + col)) : 0u;
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ float4 op_apply(const Operand &o, const RawVec &r, long long row, long long nrows, int col,
+                                           const float *s_s, const float *s_t, const float *s_p) {
+    if (MODE == 0) return r.a;
+    const bool ok = row < nrows && col < o.ncols;
+    if (!ok) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 s = *reinterpret_cast<const float4 *>(s_s + col), t = *reinterpret_cast<const float4 *>(s_t + col);
+    float4 v;
+    v.x = fmaf(r.a.x, s.x, t.x), v.y = fmaf(r.a.y, s.y, t.y), v.z = fmaf(r.a.z, s.z, t.z), v.w = fmaf(r.a.w, s.w, t.w);
+    if (MODE == 1) {
+        v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+    } else if (MODE == 2) {
+        const uint32_t k = (uint32_t)row & (uint32_t)(o.S - 1);
+        v.x = (((r.arg) & 0xffu) == k ? r.a2.x : 0.f) - v.x;
+        v.y = (((r.arg >> 8) & 0xffu) == k ? r.a2.y : 0.f) - v.y;
+        v.z = (((r.arg >> 16) & 0xffu) == k ? r.a2.z : 0.f) - v.z;
+        v.w = (((r.arg >> 24) & 0xffu) == k ? r.a2.w : 0.f) - v.w;
+    } else {  // MODE == 3
+        const float4 p = *reinterpret_cast<const float4 *>(s_p + col);
+        v.x = fmaf(r.a2.x, p.x, -v.x), v.y = fmaf(r.a2.y, p.y, -v.y), v.z = fmaf(r.a2.z, p.z, -v.z),
+        v.w = fmaf(r.a2.w, p.w, -v.w);
+    }
+    return v;
+}
+
+// One lane polls the mbarrier, the rest of the warp waits at the warp barrier: 32x fewer try_wait requests hit
+// the barrier unit (with every thread polling, the waits themselves were the top stall in the first ncu capture).
+__device__ __forceinline__ void mbar_wait_warp(int lane, uint32_t bar, uint32_t parity) {
+    if (lane == 0) tc::mbar_wait(bar, parity);
+    __syncwarp();
+}
+
+__device__ __forceinline__ void split4(const float4 &v, float4 &hi, float4 &lo) {
+    tc::split_tf32(v.x, hi.x, lo.x);
+    tc::split_tf32(v.y, hi.y, lo.y);
+    tc::split_tf32(v.z, hi.z, lo.z);
+    tc::split_tf32(v.w, hi.w, lo.w);
+}
+
+// ================================================================================================
+// T1: row-tile GEMM
+//   EMODE 0  store D; stats (sum d, sum d^2); optional group max/min + arg            forward layers
+//   EMODE 1  v = d * [E*es + et > 0]; store v; stats (sum v, sum v * (E*ei + em))      dZ of the inner layer
+//   EMODE 2  store D into Y(:, ycol0 : ycol0+N) with row stride ldy; no stats           dX
+struct RowGemmArgs {
+    Operand op;
+    long long R;
+    const float *wimg;       // packed weight image: [nkb][hi|lo][N rows x 128 B swizzled]
+    float *Y;                // output rows (or nullptr)
+    int ldy, ycol0;
+    double *partial;         // (gridDim.x, kEpiThreads, 2) fp64 partial sums (EMODE 0/1)
+    int S, logS;             // EMODE 0: rows per group (power of two) for the max/min reduction, 0 = none
+    const float *gamma;      // (N): sign picks max (>= 0) or min (< 0) per channel
+    float *gsel;             // (R/S, N)
+    uint8_t *garg;           // (R/S, N)
+    const float *E;          // EMODE 1: (R, N) pre-activation of the layer whose ReLU is differentiated
+    const float *es, *et, *ei, *em;   // (N) each
+};
+
+template <int N>
+struct RowSmem {
+    static constexpr int kABytes = kTileM * 128;            // one hi or lo A tile
+    static constexpr int kWBytes = N * 128;                 // one hi or lo W tile
+    static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
+    static constexpr int kCStride = N + 4;                  // padded fp32 row stride of the staged C tile
+    static constexpr int kCBytes = kTileM * kCStride * 4;
+    static constexpr int kConst = 3 * 256 * 4;              // prologue constants s, t, p
+    static constexpr int kTotal = 1024 + kStages * kStageBytes + kCBytes + kConst + 128;
+};
+
+template <int N, int PMODE, int EMODE>
+__global__ void __launch_bounds__(kMlpThreads, 1) row_gemm_kernel(RowGemmArgs p) {
+    using SM = RowSmem<N>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 1024-byte aligned (swizzle atoms)
+    uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    float *Cs = reinterpret_cast<float *>(smem + kStages * SM::kStageBytes);
+    float *s_s = reinterpret_cast<float *>(smem + kStages * SM::kStageBytes + SM::kCBytes);
+    float *s_t = s_s + 256, *s_p = s_t + 256;
+    __shared__ __align__(8) uint64_t s_bar[2 * kStages + 4];
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int K = p.op.ncols;
+    const int nkb = (K + kKB - 1) / kKB;
+    const long long ntiles = (p.R + kTileM - 1) / kTileM;
+    const uint32_t bar_full = smem_u32(&s_bar[0]), bar_empty = smem_u32(&s_bar[kStages]);
+    const uint32_t bar_tfull = smem_u32(&s_bar[2 * kStages]), bar_tempty = smem_u32(&s_bar[2 * kStages + 2]);
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            tc::mbar_init(bar_full + 8 * s, kProdWarps);
+            tc::mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(bar_tfull + 8 * a, 1);
+            tc::mbar_init(bar_tempty + 8 * a, 4);
+        }
+        tc::mbar_fence_init();
+    }
+    if (warp == kProdWarps) tc::tmem_alloc(smem_u32(&s_tmem), 2 * N);
+    if (PMODE != 0)
+        for (int k = tid; k < 256; k += kMlpThreads) {
+            s_s[k] = k < K ? p.op.s[k] : 0.f;
+            s_t[k] = k < K ? p.op.t[k] : 0.f;
+            s_p[k] = (PMODE == 3 && k < K) ? p.op.p[k] : 0.f;
+        }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem = s_tmem;
+
+    if (warp < kProdWarps) {
+        // =============================================================== producers
+        const int c = tid & 7;        // my 16-byte chunk (4 fp32 columns) of every k-block
+        const int r0 = tid >> 3;      // my rows: r0 + 32*i
+        // Flat sequence of chunks q = (my tile index, k-block).  A static ring of PD register buffers keeps PD chunks
+        // of loads in flight per thread (memory-level parallelism: 128 threads x PD x 8 x 16 B per SM), so the HBM
+        // latency of one chunk is hidden behind the transform + MMA of the previous ones.
+        constexpr int PD = (PMODE <= 1) ? 4 : 3;
+        const long long my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+        const long long total = my_tiles * nkb;
+        RawVec buf[PD][kProdRows];
+        auto issue = [&](long long q, RawVec (&dst)[kProdRows]) {
+            if (q < total) {
+                const long long tile = blockIdx.x + (q / nkb) * gridDim.x;
+                const int kb = (int)(q % nkb);
+#pragma unroll
+                for (int i = 0; i < kProdRows; ++i) op_load<PMODE>(p.op, tile * kTileM + r0 + 32 * i, p.R, kb * kKB + 4 * c, dst[i]);
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < PD; ++j) issue(j, buf[j]);
+        for (long long q0 = 0; q0 < total; q0 += PD) {
+#pragma unroll
+            for (int j = 0; j < PD; ++j) {
+                const long long it = q0 + j;
+                if (it < total) {
+                    const long long tile = blockIdx.x + (it / nkb) * gridDim.x;
+                    const int kb = (int)(it % nkb);
+                    const int stage = (int)(it % kStages);
+                    mbar_wait_warp(lane, bar_empty + 8 * stage, (uint32_t)(((it / kStages) & 1) ^ 1));
+                    uint8_t *st = smem + stage * SM::kStageBytes;
+                    if (tid == 0) {   // weight k-block: one bulk-TMA copy (hi tile followed by lo tile)
+                        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * stage),
+                                     "r"(2u * SM::kWBytes)
+                                     : "memory");
+                        tc::bulk_g2s(smem_u32(st + 2 * SM::kABytes), p.wimg + (size_t)kb * (2 * SM::kWBytes / 4),
+                                     2u * SM::kWBytes, bar_full + 8 * stage);
+                    }
+                    const int col = kb * kKB + 4 * c;
+#pragma unroll
+                    for (int i = 0; i < kProdRows; ++i) {
+                        const int r = r0 + 32 * i;
+                        const float4 v = op_apply<PMODE>(p.op, buf[j][i], tile * kTileM + r, p.R, col, s_s, s_t, s_p);
+                        float4 hi, lo;
+                        split4(v, hi, lo);
+                        const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+                        *reinterpret_cast<float4 *>(st + off) = hi;
+                        *reinterpret_cast<float4 *>(st + SM::kABytes + off) = lo;
+                    }
+                    tc::fence_proxy_async_smem();   // my smem writes -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(bar_full + 8 * stage);
+                    issue(it + PD, buf[j]);   // refill this ring slot
+                }
+            }
+        }
+    } else if (warp == kProdWarps) {
+        // =============================================================== MMA issuer
+        constexpr uint32_t idesc = tc::umma_idesc_tf32(kTileM, N);
+        long long it = 0, ti = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+            const int acc = (int)(ti & 1);
+            mbar_wait_warp(lane, bar_tempty + 8 * acc, (uint32_t)(((ti >> 1) & 1) ^ 1));
+            tc::tc_fence_after_sync();
+            const uint32_t d_tmem = tmem + (uint32_t)(acc * N);
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int stage = (int)(it % kStages);
+                mbar_wait_warp(lane, bar_full + 8 * stage, (uint32_t)((it / kStages) & 1));
+                tc::tc_fence_after_sync();
+                if (lane == 0) {
+                    const uint32_t a_hi = smem_base + stage * SM::kStageBytes, a_lo = a_hi + SM::kABytes;
+                    const uint32_t w_hi = a_hi + 2 * SM::kABytes, w_lo = w_hi + SM::kWBytes;
+#pragma unroll
+                    for (int ks = 0; ks < kKB / 8; ++ks) {
+                        const uint64_t dah = tc::umma_desc_k_sw128(a_hi + ks * 32), dal = tc::umma_desc_k_sw128(a_lo + ks * 32);
+                        const uint64_t dwh = tc::umma_desc_k_sw128(w_hi + ks * 32), dwl = tc::umma_desc_k_sw128(w_lo + ks * 32);
+                        tc::umma_tf32(d_tmem, dal, dwh, idesc, (kb | ks) != 0);   // small terms first
+                        tc::umma_tf32(d_tmem, dah, dwl, idesc, 1u);
+                        tc::umma_tf32(d_tmem, dah, dwh, idesc, 1u);
+                    }
+                    tc::umma_commit(bar_empty + 8 * stage);                      // smem stage free when these finish
+                    if (kb == nkb - 1) tc::umma_commit(bar_tfull + 8 * acc);     // accumulator ready
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // =============================================================== epilogue
+        const int e = tid - (kProdThreads + 32);   // 0..127
+        const int q = warp & 3;                    // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;             // my accumulator row
+        // column-owner mapping for the statistics / group pass
+        const int col = (N == 128) ? e : (e & (N - 1));
+        const int rbeg = (N == 128) ? 0 : (e / N) * (kTileM / (kEpiThreads / N));
+        const int rcnt = (N == 128) ? kTileM : kTileM / (kEpiThreads / N);
+        bool want_max = true;
+        if (EMODE == 0 && p.S > 0) want_max = __ldg(p.gamma + col) >= 0.f;
+        double dacc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        long long ti = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+            const int acc = (int)(ti & 1);
+            mbar_wait_warp(lane, bar_tfull + 8 * acc, (uint32_t)((ti >> 1) & 1));
+            tc::tc_fence_after_sync();
+#pragma unroll
+            for (int ch = 0; ch < N / 32; ++ch) {
+                uint32_t v[32];
+                tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N + ch * 32), v);
+                tc::tmem_ld_wait();
+                float4 *dst = reinterpret_cast<float4 *>(Cs + row * SM::kCStride + ch * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                         __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
+            tc::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(bar_tempty + 8 * acc);   // accumulator may be overwritten
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+
+            const long long row0 = tile * kTileM;
+            const int nvalid = (int)min((long long)kTileM, p.R - row0);
+            constexpr int kVecPerRow = N / 4;
+            constexpr int kRowStep = kEpiThreads / kVecPerRow;   // rows between two float4 items of one thread
+            if (EMODE == 1) {
+                // ReLU mask of the inner layer from its pre-activation E (one coalesced read of E), store of dz,
+                // and the two BatchNorm-backward reductions -- every thread owns 4 fixed columns in this pass
+                const int cc = (e % kVecPerRow) * 4;
+                const float4 sv = __ldg(reinterpret_cast<const float4 *>(p.es + cc)), tv = __ldg(reinterpret_cast<const float4 *>(p.et + cc));
+                const float4 iv = __ldg(reinterpret_cast<const float4 *>(p.ei + cc)), mv = __ldg(reinterpret_cast<const float4 *>(p.em + cc));
+                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+                for (int rb = e / kVecPerRow; rb < nvalid; rb += 4 * kRowStep) {
+                    float4 ev[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = rb + u * kRowStep;
+                        ev[u] = r < nvalid ? __ldg(reinterpret_cast<const float4 *>(p.E + (row0 + r) * N + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = rb + u * kRowStep;
+                        if (r < nvalid) {
+                            float4 dv = *reinterpret_cast<const float4 *>(Cs + r * SM::kCStride + cc);
+                            dv.x = fmaf(ev[u].x, sv.x, tv.x) > 0.f ? dv.x : 0.f;
+                            dv.y = fmaf(ev[u].y, sv.y, tv.y) > 0.f ? dv.y : 0.f;
+                            dv.z = fmaf(ev[u].z, sv.z, tv.z) > 0.f ? dv.z : 0.f;
+                            dv.w = fmaf(ev[u].w, sv.w, tv.w) > 0.f ? dv.w : 0.f;
+                            *reinterpret_cast<float4 *>(p.Y + (row0 + r) * p.ldy + p.ycol0 + cc) = dv;
+                            a0.x += dv.x, a0.y += dv.y, a0.z += dv.z, a0.w += dv.w;
+                            a1.x = fmaf(dv.x, fmaf(ev[u].x, iv.x, mv.x), a1.x);
+                            a1.y = fmaf(dv.y, fmaf(ev[u].y, iv.y, mv.y), a1.y);
+                            a1.z = fmaf(dv.z, fmaf(ev[u].z, iv.z, mv.z), a1.z);
+                            a1.w = fmaf(dv.w, fmaf(ev[u].w, iv.w, mv.w), a1.w);
+                        }
+                    }
+                }
+                dacc[0] += a0.x, dacc[1] += a0.y, dacc[2] += a0.z, dacc[3] += a0.w;
+                dacc[4] += a1.x, dacc[5] += a1.y, dacc[6] += a1.z, dacc[7] += a1.w;
+            } else if (p.Y) {   // coalesced store of the tile: 16 bytes per thread per step
+                for (int v4 = e; v4 < nvalid * kVecPerRow; v4 += kEpiThreads) {
+                    const int r = v4 / kVecPerRow, cc = (v4 % kVecPerRow) * 4;
+                    *reinterpret_cast<float4 *>(p.Y + (row0 + r) * p.ldy + p.ycol0 + cc) =
+                        *reinterpret_cast<const float4 *>(Cs + r * SM::kCStride + cc);
+                }
+            }
+            if (EMODE == 0) {   // per-channel statistics (+ group max/min) by the column owners, 8 rows per batch
+                const int rend = min(rbeg + rcnt, nvalid);
+                const int smask = p.S > 0 ? p.S - 1 : 0;
+                float s = 0.f, sq = 0.f, best = 0.f;
+                int bi = 0;
+                for (int r = rbeg; r < rend; r += 8) {
+                    float y[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) y[u] = (r + u < rend) ? Cs[(r + u) * SM::kCStride + col] : 0.f;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (r + u < rend) {
+                            s += y[u], sq = fmaf(y[u], y[u], sq);
+                            if (p.S > 0) {
+                                const int k = (r + u) & smask;
+                                const bool better = (k == 0) || (want_max ? (y[u] > best) : (y[u] < best));
+                                if (better) best = y[u], bi = k;
+                                if (k == smask) {
+                                    const long long g = (row0 + r + u) >> p.logS;
+                                    p.gsel[g * N + col] = best;
+                                    p.garg[g * N + col] = (uint8_t)bi;
+                                }
+                            }
+                        }
+                    }
+                }
+                dacc[0] += (double)s, dacc[1] += (double)sq;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // Cs is reused by the next tile
+        }
+        if (EMODE == 0) {
+            p.partial[((size_t)blockIdx.x * kEpiThreads + e) * 2 + 0] = dacc[0];
+            p.partial[((size_t)blockIdx.x * kEpiThreads + e) * 2 + 1] = dacc[1];
+        } else if (EMODE == 1) {
+            // fold the per-thread (4 columns x 2) fp64 sums into one pair per column, in a fixed order
+            constexpr int kVecPerRow = N / 4;
+            double *sd = reinterpret_cast<double *>(Cs);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sd[e * 8 + j] = dacc[j];
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            double t0 = 0.0, t1 = 0.0;
+            if (e < N) {
+                for (int u = 0; u < kEpiThreads / kVecPerRow; ++u) {
+                    const int t = (e >> 2) + kVecPerRow * u;
+                    t0 += sd[t * 8 + (e & 3)], t1 += sd[t * 8 + 4 + (e & 3)];
+                }
+            }
+            p.partial[((size_t)blockIdx.x * kEpiThreads + e) * 2 + 0] = t0;
+            p.partial[((size_t)blockIdx.x * kEpiThreads + e) * 2 + 1] = t1;
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kProdWarps) tc::tmem_dealloc(tmem, 2 * N);
+}
+
+// ================================================================================================
+// T2: weight gradient  D[M=128, N] = sum over row tiles of P(tile)^T * Q(tile),  K = rows.
+// Both operands are staged ROW-major exactly like a T1 A tile (coalesced loads, 16-byte swizzled stores) and
+// handed to the tensor core as MN-major operands (the 128-byte lines run along M / N, the 8-line atoms along K).
+// Each CTA owns a contiguous range of row tiles, keeps D in TMEM for the whole kernel and finally writes its
+// partial (M x N) to HBM; wgrad_reduce_kernel sums the partials in a fixed order (deterministic).
+struct WgradArgs {
+    Operand P, Q;            // P: (R, 128) -> M = 128 channels (zero beyond P.ncols); Q: (R, N)
+    long long R;
+    float *partial;          // (gridDim.x, 128, N)
+    uint32_t d_lbo, d_sbo, d_type, d_kstep;   // MN-major descriptor fields (bytes / layout type)
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;   // next 32-element chunk along M/N
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;   // next 8-line atom along K
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)type << 61;
+    return d;
+}
+
+// MN-major operand tile for 32-bit elements: the tensor core only accepts the "128-byte swizzle with 32-byte
+// atomicity" layout here (layout type 1; with the 16-byte-atom types 0/2 a tf32 MN-major MMA yields zeros --
+// measured, profiles/README.md).  Element (k-line r in [0,32), float4 column c4 along M/N):
+//   32-channel block (c4 / 8) * 4096  +  line r * 128  +  32-byte chunk ((c4 % 8) / 2) ^ (r % 4)  +  (c4 % 2) * 16
+__device__ __forceinline__ uint32_t mn_b32_offset(int r, int c4) {
+    return (uint32_t)((c4 >> 3) * 4096 + r * 128 + (((((c4 & 7) >> 1) ^ (r & 3)) << 5) | ((c4 & 1) << 4)));
+}
+
+template <int N>
+struct WgSmem {
+    static constexpr int kPBytes = 4 * 4096;                // 4 chunks of 32 channels x (32 k-lines x 128 B)
+    static constexpr int kQBytes = (N / 32) * 4096;
+    static constexpr int kStageBytes = 2 * kPBytes + 2 * kQBytes;
+    static constexpr int kConst = 6 * 256 * 4;
+    static constexpr int kTotal = 1024 + kStages * kStageBytes + kConst + 128;
+};
+
+template <int N, int PMODE, int QMODE>
+__global__ void __launch_bounds__(kMlpThreads, 1) wgrad_kernel(WgradArgs p) {
+    using SM = WgSmem<N>;
+    constexpr int kTmemCols = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    float *cst = reinterpret_cast<float *>(smem + kStages * SM::kStageBytes);
+    float *ps = cst, *pt = cst + 256, *pp = cst + 512, *qs = cst + 768, *qt = cst + 1024, *qp = cst + 1280;
+    __shared__ __align__(8) uint64_t s_bar[2 * kStages + 1];
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long ntiles = (p.R + kTileM - 1) / kTileM;
+    const long long per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const long long t_beg = min(ntiles, (long long)blockIdx.x * per), t_end = min(ntiles, t_beg + per);
+    const long long nkb_total = (t_end - t_beg) * (kTileM / kKB);   // k-blocks of 32 rows
+    const uint32_t bar_full = smem_u32(&s_bar[0]), bar_empty = smem_u32(&s_bar[kStages]);
+    const uint32_t bar_done = smem_u32(&s_bar[2 * kStages]);
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            tc::mbar_init(bar_full + 8 * s, kProdWarps);
+            tc::mbar_init(bar_empty + 8 * s, 1);
+        }
+        tc::mbar_init(bar_done, 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == kProdWarps) tc::tmem_alloc(smem_u32(&s_tmem), kTmemCols);
+    for (int k = tid; k < 256; k += kMlpThreads) {
+        ps[k] = (PMODE != 0 && k < p.P.ncols) ? p.P.s[k] : 0.f;
+        pt[k] = (PMODE != 0 && k < p.P.ncols) ? p.P.t[k] : 0.f;
+        pp[k] = (PMODE == 3 && k < p.P.ncols) ? p.P.p[k] : 0.f;
+        qs[k] = (QMODE != 0 && k < p.Q.ncols) ? p.Q.s[k] : 0.f;
+        qt[k] = (QMODE != 0 && k < p.Q.ncols) ? p.Q.t[k] : 0.f;
+        qp[k] = 0.f;
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem = s_tmem;
+
+    if (warp < kProdWarps) {
+        // producers: k-block = 32 rows.  P slab: 32 rows x 128 channels = 1024 float4 (8 per thread);
+        // Q slab: 32 rows x N channels = 8N float4.  Two k-blocks of loads are kept in flight per thread.
+        constexpr int kQVec = N / 4;                    // float4 per Q row
+        constexpr int kQItems = (32 * kQVec + kProdThreads - 1) / kProdThreads;
+        constexpr int PD = 2;                           // k-blocks of loads in flight per thread (register ring)
+        constexpr int kPItems = 32 * 32 / kProdThreads;   // float4 of the P slab per thread
+        const int pc4 = tid & 31, pr0 = tid >> 5;       // P: my float4 column, rows pr0 + kProdWarps*i
+        RawVec pv[PD][kPItems], qv[PD][kQItems];
+        auto issue = [&](long long kbk, RawVec (&pd)[kPItems], RawVec (&qd)[kQItems]) {
+            if (kbk < nkb_total) {
+                const long long row_base = t_beg * kTileM + kbk * kKB;
+#pragma unroll
+                for (int i = 0; i < kPItems; ++i) op_load<PMODE>(p.P, row_base + pr0 + kProdWarps * i, p.R, 4 * pc4, pd[i]);
+#pragma unroll
+                for (int i = 0; i < kQItems; ++i) {
+                    const int item = tid + kProdThreads * i;
+                    const int r = item / kQVec, c4 = item % kQVec;
+                    if (item < 32 * kQVec) op_load<QMODE>(p.Q, row_base + r, p.R, 4 * c4, qd[i]);
+                }
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < PD; ++j) issue(j, pv[j], qv[j]);
+        for (long long k0 = 0; k0 < nkb_total; k0 += PD) {
+#pragma unroll
+            for (int j = 0; j < PD; ++j) {
+                const long long kbk = k0 + j;
+                if (kbk < nkb_total) {
+                    const long long row_base = t_beg * kTileM + kbk * kKB;
+                    const int stage = (int)(kbk % kStages);
+                    mbar_wait_warp(lane, bar_empty + 8 * stage, (uint32_t)(((kbk / kStages) & 1) ^ 1));
+                    uint8_t *st = smem + stage * SM::kStageBytes;
+#pragma unroll
+                    for (int i = 0; i < kPItems; ++i) {
+                        const int r = pr0 + kProdWarps * i;
+                        const float4 v = op_apply<PMODE>(p.P, pv[j][i], row_base + r, p.R, 4 * pc4, ps, pt, pp);
+                        float4 hi, lo;
+                        split4(v, hi, lo);
+                        const uint32_t off = mn_b32_offset(r, pc4);
+                        *reinterpret_cast<float4 *>(st + off) = hi;
+                        *reinterpret_cast<float4 *>(st + SM::kPBytes + off) = lo;
+                    }
+#pragma unroll
+                    for (int i = 0; i < kQItems; ++i) {
+                        const int item = tid + kProdThreads * i;
+                        if (item < 32 * kQVec) {
+                            const int r = item / kQVec, c4 = item % kQVec;
+                            const float4 v = op_apply<QMODE>(p.Q, qv[j][i], row_base + r, p.R, 4 * c4, qs, qt, qp);
+                            float4 hi, lo;
+                            split4(v, hi, lo);
+                            const uint32_t off = mn_b32_offset(r, c4);
+                            *reinterpret_cast<float4 *>(st + 2 * SM::kPBytes + off) = hi;
+                            *reinterpret_cast<float4 *>(st + 2 * SM::kPBytes + SM::kQBytes + off) = lo;
+                        }
+                    }
+                    tc::fence_proxy_async_smem();   // my smem writes -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(bar_full + 8 * stage);
+                    issue(kbk + PD, pv[j], qv[j]);
+                }
+            }
+        }
+    } else if (warp == kProdWarps) {
+        // MMA issuer: A = P^T (M = 128 channels, MN-major), B = Q^T (N channels, MN-major), K = 8 rows per MMA
+        constexpr uint32_t idesc = tc::umma_idesc_tf32(kTileM, N) | (1u << 15) | (1u << 16);
+        for (long long kbk = 0; kbk < nkb_total; ++kbk) {
+            const int stage = (int)(kbk % kStages);
+            mbar_wait_warp(lane, bar_full + 8 * stage, (uint32_t)((kbk / kStages) & 1));
+            tc::tc_fence_after_sync();
+            if (lane == 0) {
+                const uint32_t p_hi = smem_base + stage * SM::kStageBytes, p_lo = p_hi + SM::kPBytes;
+                const uint32_t q_hi = p_hi + 2 * SM::kPBytes, q_lo = q_hi + SM::kQBytes;
+#pragma unroll
+                for (int ks = 0; ks < kKB / 8; ++ks) {   // 8 rows = one 1024-byte atom per chunk
+                    const uint32_t ko = ks * p.d_kstep;
+                    const uint64_t dph = umma_desc_mn(p_hi + ko, p.d_lbo, p.d_sbo, p.d_type), dpl = umma_desc_mn(p_lo + ko, p.d_lbo, p.d_sbo, p.d_type);
+                    const uint64_t dqh = umma_desc_mn(q_hi + ko, p.d_lbo, p.d_sbo, p.d_type), dql = umma_desc_mn(q_lo + ko, p.d_lbo, p.d_sbo, p.d_type);
+                    tc::umma_tf32(tmem, dpl, dqh, idesc, (kbk | ks) != 0);
+                    tc::umma_tf32(tmem, dph, dql, idesc, 1u);
+                    tc::umma_tf32(tmem, dph, dqh, idesc, 1u);
+                }
+                tc::umma_commit(bar_empty + 8 * stage);
+                if (kbk == nkb_total - 1) tc::umma_commit(bar_done);
+            }
+            __syncwarp();
+        }
+    } else {
+        // epilogue: once, after the last MMA -> partial (128 x N) of this CTA (zeros when it had no tile)
+        const int q = warp & 3, row = q * 32 + lane;
+        float *out = p.partial + ((size_t)blockIdx.x * kTileM + row) * N;
+        if (nkb_total > 0) {
+            mbar_wait_warp(lane, bar_done, 0u);
+            tc::tc_fence_after_sync();
+#pragma unroll
+            for (int ch = 0; ch < N / 32; ++ch) {
+                uint32_t v[32];
+                tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    reinterpret_cast<float4 *>(out + ch * 32)[j] =
+                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                    __uint_as_float(v[4 * j + 3]));
+            }
+        } else {
+            for (int j = 0; j < N / 4; ++j) reinterpret_cast<float4 *>(out)[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kProdWarps) tc::tmem_dealloc(tmem, kTmemCols);
+}
+
+// dW[m, n] = sum_cta partial[cta, m, n] for m < M, n < Nv  (fixed order -> deterministic)
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(int nparts, int M, int Nv, int N, const float *__restrict__ partial, float *__restrict__ dw, int lddw) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= M * Nv) return;
+    const int m = t / Nv, n = t % Nv;
+    float acc = 0.f;
+    for (int c = 0; c < nparts; ++c) acc += partial[((size_t)c * kTileM + m) * N + n];
+    dw[(size_t)m * lddw + n] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight image: W (N, K) fp32 -> [nkb][hi|lo][N rows x 128 B, 128-byte swizzle], zero padded to nkb*32 columns
+__global__ void __launch_bounds__(256)
+pack_weight_kernel(int N, int K, int ldw, const float *__restrict__ W, float *__restrict__ img) {
+    const int nkb = (K + kKB - 1) / kKB;
+    const int total = nkb * N * kKB;
+    for (int t = blockIdx.x * 256 + threadIdx.x; t < total; t += gridDim.x * 256) {
+        const int kb = t / (N * kKB), rem = t - kb * N * kKB, n = rem / kKB, c = rem % kKB;
+        const int k = kb * kKB + c;
+        const float w = k < K ? W[(size_t)n * ldw + k] : 0.f;
+        float hi, lo;
+        tc::split_tf32(w, hi, lo);
+        const size_t base = (size_t)kb * (2 * N * kKB);
+        const uint32_t off = tc::sw128_offset(n, c) / 4;
+        img[base + off] = hi;
+        img[base + (size_t)N * kKB + off] = lo;
+    }
+}
+
+// BatchNorm batch statistics from the per-thread fp64 partials -> scale/shift (+ saved mean / invstd, running
+// statistics update with momentum and the unbiased variance, nn.BatchNorm2d semantics).
+__global__ void bn_finalize_kernel(int N, int nparts, long long R, const double *__restrict__ partial,
+                                   const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
+                                   float momentum, float *running_mean, float *running_var, float *scale, float *shift,
+                                   float *save_mean, float *save_invstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    double s = 0.0, q = 0.0;
+    for (int i = c; i < nparts; i += N) s += partial[2 * (size_t)i], q += partial[2 * (size_t)i + 1];   // threads e with e % N == c
+    const double mean = s / (double)R;
+    double var = q / (double)R - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+    save_mean[c] = (float)mean;
+    save_invstd[c] = invstd;
+    if (running_mean) {
+        const double unbiased = R > 1 ? var * (double)R / (double)(R - 1) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+// sums of the fp64 partial pairs per channel: out[0][c] = sum of first components, out[1][c] = second
+__global__ void partial_sum_kernel(int N, int nparts, const double *__restrict__ partial, float *__restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    double s = 0.0, q = 0.0;
+    for (int i = c; i < nparts; i += N) s += partial[2 * (size_t)i], q += partial[2 * (size_t)i + 1];
+    out[c] = (float)s;
+    out[N + c] = (float)q;
+}
+
+template <int N, int PM, int EM>
+static int launch_row(const RowGemmArgs &a, int grid, cudaStream_t stream) {
+    auto kern = row_gemm_kernel<N, PM, EM>;
+    const int smem = RowSmem<N>::kTotal;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return status_of(e);
+    kern<<<grid, kMlpThreads, smem, stream>>>(a);
+    return SG4D_LAUNCH_CHECK();
+}
+
+template <int PM, int EM>
+static int launch_row_n(int n, const RowGemmArgs &a, int grid, cudaStream_t stream) {
+    return n == 128 ? launch_row<128, PM, EM>(a, grid, stream) : launch_row<64, PM, EM>(a, grid, stream);
+}
+
+template <int N, int PM, int QM>
+static int launch_wgrad(const WgradArgs &a, int grid, cudaStream_t stream) {
+    auto kern = wgrad_kernel<N, PM, QM>;
+    const int smem = WgSmem<N>::kTotal;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return status_of(e);
+    kern<<<grid, kMlpThreads, smem, stream>>>(a);
+    return SG4D_LAUNCH_CHECK();
+}
+
+template <int PM, int QM>
+static int launch_wgrad_n(int n, const WgradArgs &a, int grid, cudaStream_t stream) {
+    switch (n) {
+        case 32: return launch_wgrad<32, PM, QM>(a, grid, stream);
+        case 64: return launch_wgrad<64, PM, QM>(a, grid, stream);
+        case 128: return launch_wgrad<128, PM, QM>(a, grid, stream);
+        case 224: return launch_wgrad<224, PM, QM>(a, grid, stream);
+        default: return SG4D_EINVAL;
+    }
+}
+
+static int mlp_grid(long long rows) {
+    const long long ntiles = (rows + kTileM - 1) / kTileM;
+    return (int)(ntiles < SG4D_NUM_SMS ? (ntiles < 1 ? 1 : ntiles) : SG4D_NUM_SMS);
+}
+
+}  // namespace sg4d
+
+using namespace sg4d;
+
+extern "C" int sg4d_mlp_grid(long long rows) { return mlp_grid(rows); }
+
+extern "C" long long sg4d_weight_image_floats(int n, int k) {
+    return (long long)((k + kKB - 1) / kKB) * 2 * n * kKB;
+}
+
+extern "C" int sg4d_pack_weight(int n, int k, int ldw, const float *w, float *img, sg4d_stream_t stream) {
+    if (n <= 0 || k <= 0 || ldw < k || (n & 7) || !w || !img) return SG4D_EINVAL;
+    const int total = ((k + kKB - 1) / kKB) * n * kKB;
+    pack_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, k, ldw, w, img);
+    return SG4D_LAUNCH_CHECK();
+}
+
+static int ilog2(int v) {
+    int l = 0;
+    while ((1 << (l + 1)) <= v) ++l;
+    return l;
+}
+static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+static bool row_common_ok(long long rows, int k, int lda, int n) {
+    return rows > 0 && k > 0 && k <= 256 && !(k & 3) && lda >= k && !(lda & 3) && (n == 64 || n == 128);
+}
+
+extern "C" int sg4d_linear_fwd(long long rows, int k, int lda, int n, int group, const float *a, const float *scale,
+                               const float *shift, const float *wimg, float *y, double *partial, const float *gamma,
+                               float *gsel, uint8_t *garg, sg4d_stream_t stream) {
+    if (!row_common_ok(rows, k, lda, n) || !a || !wimg || !partial || (scale && !shift)) return SG4D_EINVAL;
+    if (group != 0 && (group < 1 || group > 128 || (128 % group) || (n == 64 && group > 64) || rows % group || !gamma ||
+                       !gsel || !garg))
+        return SG4D_EINVAL;
+    RowGemmArgs args{};
+    args.op.A = a, args.op.lda = lda, args.op.s = scale, args.op.t = shift, args.op.ncols = k;
+    args.R = rows, args.wimg = wimg, args.Y = y, args.ldy = n, args.ycol0 = 0, args.partial = partial;
+    args.S = group, args.logS = ilog2(group), args.gamma = gamma, args.gsel = gsel, args.garg = garg;
+    const int grid = mlp_grid(rows);
+    return scale ? launch_row_n<1, 0>(n, args, grid, (cudaStream_t)stream)
+                 : launch_row_n<0, 0>(n, args, grid, (cudaStream_t)stream);
+}
+
+extern "C" int sg4d_pool_bwd_da(long long rows, int k, int n, int group, const float *y2, const float *a2, const float *b2,
+                                const float *dsel, const uint8_t *garg, const float *wimg_t, const float *y1,
+                                const float *es, const float *et, const float *ei, const float *em, float *dz1,
+                                double *partial, sg4d_stream_t stream) {
+    if (!row_common_ok(rows, k, k, n) || !pow2(group) || group > 128 || rows % group || !y2 || !a2 || !b2 || !dsel || !garg ||
+        !wimg_t || !y1 || !es || !et || !ei || !em || !dz1 || !partial)
+        return SG4D_EINVAL;
+    RowGemmArgs args{};
+    args.op.A = y2, args.op.lda = k, args.op.s = a2, args.op.t = b2, args.op.dsel = dsel, args.op.garg = garg;
+    args.op.S = group, args.op.logS = ilog2(group), args.op.ldsel = k, args.op.ncols = k;
+    args.R = rows, args.wimg = wimg_t, args.Y = dz1, args.ldy = n, args.ycol0 = 0, args.partial = partial;
+    args.E = y1, args.es = es, args.et = et, args.ei = ei, args.em = em;
+    return launch_row_n<2, 1>(n, args, mlp_grid(rows), (cudaStream_t)stream);
+}
+
+extern "C" int sg4d_inner_bwd_dx(long long rows, int k, int n, const float *y1, const float *dz1, const float *p1,
+                                 const float *q1, const float *u1, const float *wimg_t, float *dx, int lddx, int col0,
+                                 sg4d_stream_t stream) {
+    if (!row_common_ok(rows, k, k, n) || !y1 || !dz1 || !p1 || !q1 || !u1 || !wimg_t || !dx || (lddx & 3) || (col0 & 3) ||
+        col0 < 0 || col0 + n > lddx)
+        return SG4D_EINVAL;
+    RowGemmArgs args{};
+    args.op.A = y1, args.op.lda = k, args.op.A2 = dz1, args.op.lda2 = k, args.op.s = q1, args.op.t = u1, args.op.p = p1;
+    args.op.ncols = k;
+    args.R = rows, args.wimg = wimg_t, args.Y = dx, args.ldy = lddx, args.ycol0 = col0;
+    return launch_row_n<3, 2>(n, args, mlp_grid(rows), (cudaStream_t)stream);
+}
+
+static int wgrad_common(long long rows, int m, int nq, int npad, float *partial, float *dw, int lddw, WgradArgs &args,
+                        int pmode, int qmode, cudaStream_t stream) {
+    const int grid = mlp_grid(rows);
+    args.R = rows, args.partial = partial;
+    // LBO = next 32-channel block, SBO = next 4-line swizzle atom, layout type 1 = SWIZZLE_128B_BASE32B, 8 k-lines per MMA
+    args.d_lbo = 4096, args.d_sbo = 512, args.d_type = 1, args.d_kstep = 1024;
+    int st;
+    if (pmode == 2 && qmode == 1) st = launch_wgrad_n<2, 1>(npad, args, grid, stream);
+    else if (pmode == 3 && qmode == 0) st = launch_wgrad_n<3, 0>(npad, args, grid, stream);
+    else st = SG4D_EINVAL;
+    if (st != SG4D_OK) return st;
+    wgrad_reduce_kernel<<<(m * nq + 255) / 256, 256, 0, stream>>>(grid, m, nq, npad, partial, dw, lddw);
+    return SG4D_LAUNCH_CHECK();
+}
+
+extern "C" long long sg4d_wgrad_partial_floats(long long rows, int npad) { return (long long)mlp_grid(rows) * kTileM * npad; }
+
+extern "C" int sg4d_pool_bwd_dw(long long rows, int m, int n, int group, const float *y2, const float *a2, const float *b2,
+                                const float *dsel, const uint8_t *garg, const float *y1, const float *s1, const float *t1,
+                                float *partial, float *dw, sg4d_stream_t stream) {
+    if (rows <= 0 || (m != 64 && m != 128) || (n != 64 && n != 128) || !pow2(group) || group > 128 || rows % group || !y2 || !a2 ||
+        !b2 || !dsel || !garg || !y1 || !s1 || !t1 || !partial || !dw)
+        return SG4D_EINVAL;
+    WgradArgs args{};
+    args.P.A = y2, args.P.lda = m, args.P.s = a2, args.P.t = b2, args.P.dsel = dsel, args.P.garg = garg, args.P.S = group, args.P.logS = ilog2(group);
+    args.P.ldsel = m, args.P.ncols = m;
+    args.Q.A = y1, args.Q.lda = n, args.Q.s = s1, args.Q.t = t1, args.Q.ncols = n;
+    return wgrad_common(rows, m, n, n, partial, dw, n, args, 2, 1, (cudaStream_t)stream);
+}
+
+extern "C" int sg4d_inner_bwd_dw(long long rows, int m, int k, int ldx, const float *y1, const float *dz1, const float *p1,
+                                 const float *q1, const float *u1, const float *x, float *partial, float *dw,
+                                 sg4d_stream_t stream) {
+    if (rows <= 0 || (m != 64 && m != 128) || k <= 0 || k > 224 || ldx < k || (ldx & 3) || !y1 || !dz1 || !p1 || !q1 || !u1 ||
+        !x || !partial || !dw)
+        return SG4D_EINVAL;
+    const int npad = k <= 32 ? 32 : (k <= 64 ? 64 : (k <= 128 ? 128 : 224));
+    WgradArgs args{};
+    args.P.A = y1, args.P.lda = m, args.P.A2 = dz1, args.P.lda2 = m, args.P.s = q1, args.P.t = u1, args.P.p = p1;
+    args.P.ncols = m;
+    args.Q.A = x, args.Q.lda = ldx, args.Q.ncols = (k + 3) & ~3;
+    return wgrad_common(rows, m, k, npad, partial, dw, k, args, 3, 0, (cudaStream_t)stream);
+}
+
+extern "C" int sg4d_bn_finalize(int n, int nparts, long long rows, const double *partial, const float *gamma,
+                                const float *beta, float eps, float momentum, float *running_mean, float *running_var,
+                                float *scale, float *shift, float *save_mean, float *save_invstd, sg4d_stream_t stream) {
+    if (n <= 0 || nparts <= 0 || rows <= 0 || !partial || !gamma || !beta || !scale || !shift || !save_mean || !save_invstd)
+        return SG4D_EINVAL;
+    bn_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, nparts, rows, partial, gamma, beta, eps, momentum,
+                                                                       running_mean, running_var, scale, shift, save_mean,
+                                                                       save_invstd);
+    return SG4D_LAUNCH_CHECK();
+}
+
+extern "C" int sg4d_partial_sums(int n, int nparts, const double *partial, float *out, sg4d_stream_t stream) {
+    if (n <= 0 || nparts <= 0 || !partial || !out) return SG4D_EINVAL;
+    partial_sum_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, nparts, partial, out);
+    return SG4D_LAUNCH_CHECK();
+}

@@ -1,0 +1,189 @@
+"""Fused shared point-MLP of one set-abstraction scale on the tensor cores (``csrc/mlp.cu``).
+
+``fused_shared_mlp(x, k0, group, mlp)`` evaluates the reference's
+``[Conv2d(1x1) -> BatchNorm2d -> ReLU] x 2 -> max_pool2d over nsample`` (OPS/pointnet2_modules.py:9-19,
+66-70) on the point-major grouped matrix ``x (R, K_padded)`` and returns the pooled ``(R / group, C_out)``
+features, forward and backward:
+
+  forward   2 x sg4d_linear_fwd (3xTF32 tcgen05 GEMM; BatchNorm+ReLU of the previous layer fused into the
+            operand staging, statistics and max-pool fused into the epilogue) + 2 x sg4d_bn_finalize
+  backward  sg4d_pool_bwd_da / sg4d_pool_bwd_dw / sg4d_inner_bwd_dw (/ sg4d_inner_bwd_dx): the max-pool, ReLU and
+            BatchNorm backward formulas are evaluated inside the operand stagers from the saved pre-activations
+            y1, y2 and a handful of per-channel constants computed here -- no dY tensor is ever materialised.
+
+Saved for backward: x, y1, y2 (pre-activations), the pooled selection (value + row index) and per-channel vectors.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+
+def pack_weight(w2d):
+    """(N, K) fp32 -> the pre-split, pre-swizzled shared-memory image sg4d_linear_fwd streams by bulk TMA."""
+    w2d = w2d.contiguous()
+    n, k = w2d.shape
+    img = torch.empty(_lib.load().sg4d_weight_image_floats(n, k), dtype=torch.float32, device=w2d.device)
+    _lib.call("sg4d_pack_weight", w2d, n, k, w2d.stride(0), w2d.data_ptr(), img.data_ptr())
+    return img
+
+
+def linear_fwd(a, k, wimg, n, scale=None, shift=None, group=0, gamma=None, store_y=True):
+    """Y = act(a[:, :k]) @ W^T with fused statistics (and group max/min).  Returns (y, partial, gsel, garg)."""
+    rows, lda = a.shape
+    dev = a.device
+    y = torch.empty(rows, n, dtype=torch.float32, device=dev) if store_y else None
+    grid = _lib.load().sg4d_mlp_grid(rows)
+    partial = torch.empty(grid * 128 * 2, dtype=torch.float64, device=dev)
+    gsel = garg = None
+    if group:
+        gsel = torch.empty(rows // group, n, dtype=torch.float32, device=dev)
+        garg = torch.empty(rows // group, n, dtype=torch.uint8, device=dev)
+    _lib.call("sg4d_linear_fwd", a, rows, k, lda, n, group, a.data_ptr(), _lib.ptr(scale), _lib.ptr(shift),
+              wimg.data_ptr(), _lib.ptr(y), partial.data_ptr(), _lib.ptr(gamma), _lib.ptr(gsel), _lib.ptr(garg))
+    return y, partial, gsel, garg
+
+
+def bn_scale_shift(bn, partial, rows):
+    """Batch statistics -> (scale, shift, mean, invstd); updates the module's running statistics exactly like
+    nn.BatchNorm2d.forward in training mode.  In eval mode the running statistics are used instead."""
+    n = bn.num_features
+    dev = bn.weight.device
+    if bn.training or not bn.track_running_stats:
+        out = torch.empty(4, n, dtype=torch.float32, device=dev)
+        track = bn.training and bn.track_running_stats
+        momentum = 0.0 if bn.momentum is None else bn.momentum
+        if track and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+            if bn.momentum is None:
+                momentum = 1.0 / float(bn.num_batches_tracked)
+        _lib.call("sg4d_bn_finalize", partial, n, partial.numel() // 2, rows, partial.data_ptr(), bn.weight.data_ptr(),
+                  bn.bias.data_ptr(), float(bn.eps), float(momentum), _lib.ptr(bn.running_mean if track else None),
+                  _lib.ptr(bn.running_var if track else None), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                  out[3].data_ptr())
+        return out[0], out[1], out[2], out[3]
+    invstd = torch.rsqrt(bn.running_var + bn.eps)
+    scale = bn.weight.detach() * invstd
+    return scale, bn.bias.detach() - bn.running_mean * scale, bn.running_mean, invstd
+
+
+def supported(mlp, k_padded, group):
+    """True when the scale can run on the fused tensor-core path (otherwise the generic path is used)."""
+    if len(mlp) != 6:
+        return False
+    c1, b1, r1, c2, b2, r2 = mlp
+    if not (isinstance(c1, nn.Conv2d) and isinstance(b1, nn.BatchNorm2d) and isinstance(c2, nn.Conv2d)
+            and isinstance(b2, nn.BatchNorm2d) and isinstance(r1, nn.ReLU) and isinstance(r2, nn.ReLU)):
+        return False
+    if c1.bias is not None or c2.bias is not None or not b1.affine or not b2.affine:
+        return False
+    n1, n2 = c1.out_channels, c2.out_channels
+    if n1 not in (64, 128) or n2 not in (64, 128) or k_padded > 224 or k_padded % 4:
+        return False
+    if group not in (1, 2, 4, 8, 16, 32, 64, 128) or (n2 == 64 and group > 64):
+        return False
+    return True
+
+
+def _wgrad_partial(rows, npad, dev):
+    return torch.empty(_lib.load().sg4d_wgrad_partial_floats(rows, npad), dtype=torch.float32, device=dev)
+
+
+class _FusedSharedMLP(torch.autograd.Function):
+    """x (R, kp); w1 (n1, kp) already permuted / zero-padded to x's column layout; w2 (n2, n1)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, g1, be1, w2, g2, be2, group, dx_cols, bn1, bn2):
+        rows, kp = x.shape
+        n1, n2 = w1.shape[0], w2.shape[0]
+        y1, part1, _, _ = linear_fwd(x, kp, pack_weight(w1), n1)
+        s1, t1, m1, i1 = bn_scale_shift(bn1, part1, rows)
+        y2, part2, gsel, garg = linear_fwd(y1, n1, pack_weight(w2), n2, scale=s1, shift=t1, group=group, gamma=g2)
+        s2, t2, m2, i2 = bn_scale_shift(bn2, part2, rows)
+        out = torch.relu(torch.addcmul(t2, gsel, s2))
+        ctx.save_for_backward(x, y1, y2, gsel, garg, out, w1, w2, s1, t1, m1, i1, s2, m2, i2)
+        ctx.meta = (group, dx_cols, bn1.training or not bn1.track_running_stats,
+                    bn2.training or not bn2.track_running_stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, y1, y2, gsel, garg, out, w1, w2, s1, t1, m1, i1, s2, m2, i2 = ctx.saved_tensors
+        group, dx_cols, batch1, batch2 = ctx.meta
+        rows, kp = x.shape
+        n1, n2 = w1.shape[0], w2.shape[0]
+        dev = x.device
+        inv_r = 1.0 / rows
+
+        # ---- layer 2: BatchNorm2 + ReLU + max-pool.  dY2 = dsel*[row is the pooled one] - (a2*y2 + b2)
+        dz = d_out * (out > 0)                                   # (G, n2) gradient at the selected rows
+        d_be2 = dz.sum(0)
+        d_g2 = (dz * ((gsel - m2) * i2)).sum(0)
+        if batch2:
+            a2 = s2 * d_g2 * i2 * inv_r
+            b2 = s2 * d_be2 * inv_r - a2 * m2
+        else:
+            a2 = torch.zeros_like(s2)
+            b2 = torch.zeros_like(s2)
+        dsel = (dz * s2).contiguous()
+        em1 = (-m1 * i1).contiguous()
+        dz1 = torch.empty(rows, n1, dtype=torch.float32, device=dev)
+        part = torch.empty(_lib.load().sg4d_mlp_grid(rows) * 128 * 2, dtype=torch.float64, device=dev)
+        _lib.call("sg4d_pool_bwd_da", x, rows, n2, n1, group, y2.data_ptr(), a2.data_ptr(), b2.data_ptr(), dsel.data_ptr(),
+                  garg.data_ptr(), pack_weight(w2.t()).data_ptr(), y1.data_ptr(), s1.data_ptr(), t1.data_ptr(),
+                  i1.data_ptr(), em1.data_ptr(), dz1.data_ptr(), part.data_ptr())
+        sums = torch.empty(2, n1, dtype=torch.float32, device=dev)
+        _lib.call("sg4d_partial_sums", x, n1, part.numel() // 2, part.data_ptr(), sums.data_ptr())
+        d_be1, d_g1 = sums[0], sums[1]
+        d_w2 = torch.empty(n2, n1, dtype=torch.float32, device=dev)
+        _lib.call("sg4d_pool_bwd_dw", x, rows, n2, n1, group, y2.data_ptr(), a2.data_ptr(), b2.data_ptr(), dsel.data_ptr(),
+                  garg.data_ptr(), y1.data_ptr(), s1.data_ptr(), t1.data_ptr(), _wgrad_partial(rows, n1, dev).data_ptr(),
+                  d_w2.data_ptr())
+
+        # ---- layer 1: dY1 = p1*dz1 - (q1*y1 + u1)
+        p1 = s1.contiguous()
+        if batch1:
+            q1 = s1 * d_g1 * i1 * inv_r
+            u1 = s1 * d_be1 * inv_r - q1 * m1
+        else:
+            q1 = torch.zeros_like(s1)
+            u1 = torch.zeros_like(s1)
+        npad = 32 if kp <= 32 else (64 if kp <= 64 else (128 if kp <= 128 else 224))
+        d_w1 = torch.empty(n1, kp, dtype=torch.float32, device=dev)
+        _lib.call("sg4d_inner_bwd_dw", x, rows, n1, kp, kp, y1.data_ptr(), dz1.data_ptr(), p1.data_ptr(), q1.data_ptr(),
+                  u1.data_ptr(), x.data_ptr(), _wgrad_partial(rows, npad, dev).data_ptr(), d_w1.data_ptr())
+        d_x = None
+        if ctx.needs_input_grad[0]:
+            # only the first dx_cols columns (the gathered features) carry a gradient downstream
+            d_x = torch.empty(rows, kp, dtype=torch.float32, device=dev)
+            d_x[:, dx_cols:].zero_()
+            col = 0
+            while col < dx_cols:
+                n = 128 if dx_cols - col >= 128 else 64
+                assert dx_cols - col >= n, "feature width must be a multiple of 64"
+                wt = pack_weight(w1[:, col:col + n].t())
+                _lib.call("sg4d_inner_bwd_dx", x, rows, n1, n, y1.data_ptr(), dz1.data_ptr(), p1.data_ptr(), q1.data_ptr(),
+                          u1.data_ptr(), wt.data_ptr(), d_x.data_ptr(), kp, col)
+                col += n
+        return (d_x, d_w1, d_g1, d_be1, d_w2, d_g2, d_be2, None, None, None, None)
+
+
+def fused_shared_mlp(x, k0, group, mlp, xyz_last=False):
+    """x (R, K_padded) point-major grouped rows -> pooled (R / group, C_out).
+
+    Column layout of x: [xyz(3) | feats(k0-3) | 0-pad] or, with xyz_last, [feats(k0-3) | xyz(3) | 0-pad]; the
+    first conv's weight columns are permuted / padded to match (differentiable torch ops, so the parameter
+    gradient comes back in the reference's channel order)."""
+    c1, b1, _, c2, b2, _ = mlp
+    kp = x.shape[1]
+    w1 = c1.weight.view(c1.out_channels, k0)
+    if xyz_last:
+        w1 = torch.cat([w1[:, 3:], w1[:, :3]], dim=1)
+    if kp != k0:
+        w1 = F.pad(w1, (0, kp - k0))
+    dx_cols = (k0 - 3) if (xyz_last and x.requires_grad) else 0
+    if x.requires_grad and not xyz_last:
+        raise RuntimeError("input gradients need the feature-first (xyz_last) column layout")
+    return _FusedSharedMLP.apply(x, w1, b1.weight, b1.bias, c2.weight.view(c2.out_channels, c2.in_channels), b2.weight,
+                                 b2.bias, int(group), int(dx_cols), b1, b2)

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import mlp as fused
 from .. import rows
 from . import pointnet2_utils
 
@@ -100,9 +101,18 @@ class _PointnetSAModuleBase(nn.Module):
             assert self.groupers[s].use_xyz, "the hot path always groups xyz (use_xyz=True)"
             k = 3 + c
             stride = 8 if k <= 8 else _pad4(k)
-            x = rows.group_rows(pts, feats, new_xyz, idx[s], cnt[s], c, feat_offset, stride)
-            y = shared_mlp_rows(mlp, x.view(-1, stride))
-            outs.append(y.view(b * self.npoint, nsamples[s], -1).amax(dim=1).view(b, self.npoint, -1))
+            needs_dx = feats is not None and feats.requires_grad and torch.is_grad_enabled()
+            use_fused = fused.supported(mlp, stride, nsamples[s]) and (not needs_dx or c % 64 == 0)
+            # feature-first column order when a gradient flows back into the gathered features (aligned dX)
+            xyz_last = use_fused and needs_dx
+            x = rows.group_rows(pts, feats, new_xyz, idx[s], cnt[s], c, feat_offset, stride, xyz_last)
+            if use_fused:
+                # tensor-core path: conv+BN+ReLU x2 + max-pool, forward and backward (csrc/mlp.cu)
+                outs.append(fused.fused_shared_mlp(x.view(-1, stride), k, nsamples[s], mlp, xyz_last)
+                            .view(b, self.npoint, -1))
+            else:
+                y = shared_mlp_rows(mlp, x.view(-1, stride))
+                outs.append(y.view(b * self.npoint, nsamples[s], -1).amax(dim=1).view(b, self.npoint, -1))
         return new_xyz, torch.cat(outs, dim=2) if len(outs) > 1 else outs[0]
 
     def forward(self, xyz: torch.Tensor, features: Optional[torch.Tensor]

@@ -58,39 +58,41 @@ class _GroupRows(torch.autograd.Function):
     backward replaces ``group_points_grad`` (:236-241) with a deterministic gather."""
 
     @staticmethod
-    def forward(ctx, pts, feats, centers, idx, cnt, c, feat_offset, out_stride):
+    def forward(ctx, pts, feats, centers, idx, cnt, c, feat_offset, out_stride, xyz_last):
         b, n, ps = pts.shape
         m, ns = idx.shape[1], idx.shape[2]
         fs = feats.shape[2] if feats is not None else ps
         out = torch.empty(b, m, ns, out_stride, dtype=torch.float32, device=pts.device)
-        _lib.call("sg4d_group_rows", pts, b, n, m, ns, c, ps, fs, feat_offset, out_stride, pts.data_ptr(),
-                  _lib.ptr(feats), centers.data_ptr(), idx.data_ptr(), out.data_ptr())
+        _lib.call("sg4d_group_rows", pts, b, n, m, ns, c, ps, fs, feat_offset, out_stride, c if xyz_last else 0,
+                  pts.data_ptr(), _lib.ptr(feats), centers.data_ptr(), idx.data_ptr(), out.data_ptr())
         ctx.save_for_backward(idx, cnt)
-        ctx.meta = (b, n, m, ns, c, fs, feat_offset, out_stride)
+        ctx.meta = (b, n, m, ns, c, fs, feat_offset, out_stride, xyz_last)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         idx, cnt = ctx.saved_tensors
-        b, n, m, ns, c, fs, feat_offset, out_stride = ctx.meta
+        b, n, m, ns, c, fs, feat_offset, out_stride, xyz_last = ctx.meta
         grad_feats = None
         if ctx.needs_input_grad[1]:
             if feat_offset != 0 or fs != c:
                 raise RuntimeError("group_rows backward expects a dense (B,n,c) feature tensor")
             grad_out = grad_out.contiguous()
             grad_feats = torch.empty(b, n, c, dtype=torch.float32, device=grad_out.device)
-            _lib.call("sg4d_group_rows_grad", grad_out, b, n, m, ns, c, out_stride, 0, grad_out.data_ptr(),
-                      idx.data_ptr(), cnt.data_ptr(), grad_feats.data_ptr())
-        return None, grad_feats, None, None, None, None, None, None
+            _lib.call("sg4d_group_rows_grad", grad_out, b, n, m, ns, c, out_stride, 0 if xyz_last else 3, 0,
+                      grad_out.data_ptr(), idx.data_ptr(), cnt.data_ptr(), grad_feats.data_ptr())
+        return None, grad_feats, None, None, None, None, None, None, None
 
 
-def group_rows(pts, feats, centers, idx, cnt, c, feat_offset=0, out_stride=None):
+def group_rows(pts, feats, centers, idx, cnt, c, feat_offset=0, out_stride=None, xyz_last=False):
+    """xyz_last=False: columns [xyz | feats | 0-pad] (the reference's channel order);
+    xyz_last=True:  columns [feats | xyz | 0-pad] (feature columns 16-byte aligned)."""
     _rows_ok(pts, "pts")
     if feats is not None:
         _rows_ok(feats, "feats")
     if out_stride is None:
         out_stride = 3 + c
-    return _GroupRows.apply(pts, feats, centers, idx, cnt, int(c), int(feat_offset), int(out_stride))
+    return _GroupRows.apply(pts, feats, centers, idx, cnt, int(c), int(feat_offset), int(out_stride), bool(xyz_last))
 
 
 # ---------------------------------------------------------------------------------------- GNN

@@ -340,7 +340,7 @@ def main_sg4d(args):
                        "l2": f"inputs are {h2d_bytes / 1e6:.0f} MB per step per GPU (> 126 MB L2), no flush needed"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
             "roofline": roof, "cpu_baseline": cpu,
-            "own_kernel_ms_per_step": own_ms, "kernels": kernels[:12]}
+            "own_kernel_ms_per_step": own_ms, "kernels": kernels[:48]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -120,9 +120,12 @@ int sg4d_ball_query_rows(int b, int n, int m, int row_stride, int center_stride,
  * pts (b,n,pts_stride) supplies xyz (columns 0..2); feats (b,n,feat_stride) supplies c channels
  * starting at column feat_offset (feats may alias pts: SA1 reads rgb/mask from the raw rows).
  * out (b,m,nsample,out_stride) with out_stride >= 3+c; columns 3+c..out_stride-1 are zeroed.
+ * xyz_col0 = 0 gives the reference's channel order (xyz first); xyz_col0 = c puts the features in columns
+ * 0..c-1 and xyz in c..c+2 (16-byte aligned feature columns for the tensor-core backward; the host side
+ * permutes the first conv's weight columns accordingly).
  * Replaces 2 x group_points + the in-place subtract + torch.cat. */
 int sg4d_group_rows(int b, int n, int m, int nsample, int c, int pts_stride, int feat_stride,
-                    int feat_offset, int out_stride, const float *pts, const float *feats,
+                    int feat_offset, int out_stride, int xyz_col0, const float *pts, const float *feats,
                     const float *centers, const int32_t *idx, float *out, sg4d_stream_t stream);
 
 /* Backward of the feature part of sg4d_group_rows (replaces group_points_grad,
@@ -130,9 +133,10 @@ int sg4d_group_rows(int b, int n, int m, int nsample, int c, int pts_stride, int
  * grad_out[b,j,k,3:3+c], accumulated in the FIXED order j ascending then k ascending
  * (deterministic; the reference's atomicAdd order is arbitrary).  Requires every idx row to be the
  * output of a ball query (ascending distinct hits followed by repeats of the first hit) and cnt
- * (b,m) from sg4d_ball_query_rows.  grad_feats (b,n,c) is fully overwritten when accumulate == 0
+ * (b,m) from sg4d_ball_query_rows; the feature gradients are columns gcol0..gcol0+c-1 of grad_out.
+ * grad_feats (b,n,c) is fully overwritten when accumulate == 0
  * and added to (the second scale of an MSG level) when accumulate != 0. */
-int sg4d_group_rows_grad(int b, int n, int m, int nsample, int c, int out_stride, int accumulate,
+int sg4d_group_rows_grad(int b, int n, int m, int nsample, int c, int out_stride, int gcol0, int accumulate,
                          const float *grad_out, const int32_t *idx, const int32_t *cnt,
                          float *grad_feats, sg4d_stream_t stream);
 
@@ -153,6 +157,69 @@ int sg4d_triplet_gather(int64_t n_edges, int d, int de, const float *x, const fl
 int sg4d_segment_sum(int n_nodes, int d, int64_t src_stride, int col0, int col1, const float *src,
                      int has_second, const int32_t *order, const int32_t *seg_ptr, float *out,
                      sg4d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Section 3 -- the shared point-MLP on the tensor cores (tcgen05, 3xTF32, fp32 accumulate in TMEM)
+ *
+ * One layer of build_shared_mlp (OPS/pointnet2_modules.py:9-19) = Conv2d(1x1, no bias) -> BatchNorm2d ->
+ * ReLU, applied to the (rows, channels) point-major matrix; the last layer of a scale is followed by
+ * max_pool2d over nsample (modules.py:67-70).  sg4d_linear_fwd computes Y = act(A) * W^T for one layer,
+ * where act() is the PREVIOUS layer's BatchNorm scale/shift + ReLU applied while the operand is staged
+ * (so normalised activations never touch HBM), and emits what this layer's BatchNorm (and the max-pool)
+ * need: per-channel sum / sum of squares and, optionally, the per-group extreme pre-activation.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* number of CTAs sg4d_linear_fwd launches for `rows` rows (= leading dimension of `partial`) */
+int sg4d_mlp_grid(long long rows);
+/* size (in floats) of the packed image of an (n, k) weight */
+long long sg4d_weight_image_floats(int n, int k);
+/* w (n, k) fp32, row stride ldw  ->  img: per 32-column k-block, the TF32 hi and lo parts as 128-byte
+ * swizzled K-major tiles (the exact shared-memory image the MMA reads; loaded by one bulk-TMA copy) */
+int sg4d_pack_weight(int n, int k, int ldw, const float *w, float *img, sg4d_stream_t stream);
+/* a (rows, lda) fp32, k valid columns (k % 4 == 0, k <= 256); scale/shift (k) or NULL (identity, no ReLU);
+ * n in {64, 128}; y (rows, n) or NULL; partial (sg4d_mlp_grid(rows), 128, 2) fp64 sums for
+ * sg4d_bn_finalize; group = nsample for the fused max-pool (0 = none; must divide 128 and rows):
+ * gsel (rows/group, n) = max (gamma[c] >= 0) or min (gamma[c] < 0) of y over the group, garg = its row. */
+int sg4d_linear_fwd(long long rows, int k, int lda, int n, int group, const float *a, const float *scale,
+                    const float *shift, const float *wimg, float *y, double *partial, const float *gamma,
+                    float *gsel, uint8_t *garg, sg4d_stream_t stream);
+/* BatchNorm2d batch statistics (nn.BatchNorm2d semantics: biased variance for normalisation, unbiased
+ * for the running estimate, momentum update; running_* may be NULL):
+ *   scale = gamma / sqrt(var + eps), shift = beta - mean * scale, save_mean, save_invstd. */
+int sg4d_bn_finalize(int n, int nparts, long long rows, const double *partial, const float *gamma,
+                     const float *beta, float eps, float momentum, float *running_mean, float *running_var,
+                     float *scale, float *shift, float *save_mean, float *save_invstd, sg4d_stream_t stream);
+
+/* ---- backward of one scale (replaces the autograd graph of conv/BN/ReLU/max_pool2d, modules.py:66-70) ----
+ * Notation: layer 1 = K0 -> C1 (pre-activation y1), layer 2 = C1 -> C2 (pre-activation y2), group = nsample.
+ * dY tensors are never materialised: the operand stagers evaluate the BatchNorm / ReLU / max-pool backward
+ * formulas on the fly from y1, y2 and per-channel constants prepared on the host side (mlp.py).          */
+
+/* dz1 = ((dY2) * W2) .* [y1*es + et > 0]   with  dY2[r,c] = dsel[r/group,c]*[r%group == garg[r/group,c]]
+ *                                                          - (a2[c]*y2[r,c] + b2[c])
+ * k = C2, n = C1; wimg_t = packed image of W2^T (n x k); also emits partial sums (sum dz1, sum dz1*yhat1),
+ * yhat1 = y1*ei + em, for sg4d_partial_sums. */
+int sg4d_pool_bwd_da(long long rows, int k, int n, int group, const float *y2, const float *a2, const float *b2,
+                     const float *dsel, const uint8_t *garg, const float *wimg_t, const float *y1,
+                     const float *es, const float *et, const float *ei, const float *em, float *dz1,
+                     double *partial, sg4d_stream_t stream);
+/* dW2 (m x n) = dY2^T * relu(y1*s1 + t1);  m = C2, n = C1;  partial: sg4d_wgrad_partial_floats(rows, n) floats */
+int sg4d_pool_bwd_dw(long long rows, int m, int n, int group, const float *y2, const float *a2, const float *b2,
+                     const float *dsel, const uint8_t *garg, const float *y1, const float *s1, const float *t1,
+                     float *partial, float *dw, sg4d_stream_t stream);
+/* dX(:, col0:col0+n) = dY1 * W1(:, cols)   with  dY1[r,c] = p1[c]*dz1[r,c] - (q1[c]*y1[r,c] + u1[c]);
+ * k = C1; wimg_t = packed image of the (n x k) slice of W1^T */
+int sg4d_inner_bwd_dx(long long rows, int k, int n, const float *y1, const float *dz1, const float *p1,
+                      const float *q1, const float *u1, const float *wimg_t, float *dx, int lddx, int col0,
+                      sg4d_stream_t stream);
+/* dW1 (m x k) = dY1^T * x(:, 0:k);  m = C1;  partial: sg4d_wgrad_partial_floats(rows, pad(k)) floats,
+ * pad(k) = 32 / 64 / 128 / 224 */
+int sg4d_inner_bwd_dw(long long rows, int m, int k, int ldx, const float *y1, const float *dz1, const float *p1,
+                      const float *q1, const float *u1, const float *x, float *partial, float *dw,
+                      sg4d_stream_t stream);
+long long sg4d_wgrad_partial_floats(long long rows, int npad);
+/* out[0:n] = sum of the first, out[n:2n] = sum of the second component of the fp64 partial pairs */
+int sg4d_partial_sums(int n, int nparts, const double *partial, float *out, sg4d_stream_t stream);
 
 #ifdef __cplusplus
 }
