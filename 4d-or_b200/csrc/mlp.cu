@@ -134,6 +134,7 @@ struct RowGemmArgs {
     uint8_t *garg;           // (R/S, N)
     const float *E;          // EMODE 1: (R, N) pre-activation of the layer whose ReLU is differentiated
     const float *es, *et, *ei, *em;   // (N) each
+    int dbg_no_tma;
 };
 
 template <int N>
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) row_gemm_kernel(RowGemmArgs p)
                     const int stage = (int)(it % kStages);
                     mbar_wait_warp(lane, bar_empty + 8 * stage, (uint32_t)(((it / kStages) & 1) ^ 1));
                     uint8_t *st = smem + stage * SM::kStageBytes;
-                    if (tid == 0) {   // weight k-block: one bulk-TMA copy (hi tile followed by lo tile)
+                    if (tid == 0 && !p.dbg_no_tma) {   // weight k-block: one bulk-TMA copy (hi tile followed by lo tile)
                         asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * stage),
                                      "r"(2u * SM::kWBytes)
                                      : "memory");
@@ -353,28 +354,64 @@ __global__ void __launch_bounds__(kMlpThreads, 1) row_gemm_kernel(RowGemmArgs p)
                         *reinterpret_cast<const float4 *>(Cs + r * SM::kCStride + cc);
                 }
             }
-            if (EMODE == 0) {   // per-channel statistics (+ group max/min) by the column owners, 8 rows per batch
-                const int rend = min(rbeg + rcnt, nvalid);
+            if (EMODE == 0) {   // per-channel statistics (+ group max/min) by the column owners
                 const int smask = p.S > 0 ? p.S - 1 : 0;
-                float s = 0.f, sq = 0.f, best = 0.f;
-                int bi = 0;
-                for (int r = rbeg; r < rend; r += 8) {
-                    float y[8];
+                float s = 0.f, sq = 0.f;
+                if (nvalid == kTileM && (p.S == 0 || p.S >= 8)) {
+                    // fast path (full tile): 8 rows per batch, branch-free, independent chains inside a batch
+                    const float sgn = want_max ? 1.f : -1.f;    // arg-min = arg-max of the negated values
+                    float s1 = 0.f, q1 = 0.f, best = 0.f;
+                    int bi = 0;
+                    for (int r = rbeg; r < rbeg + rcnt; r += 8) {
+                        float y[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) y[u] = (r + u < rend) ? Cs[(r + u) * SM::kCStride + col] : 0.f;
+                        for (int u = 0; u < 8; ++u) y[u] = Cs[(r + u) * SM::kCStride + col];
+                        s += (y[0] + y[1]) + (y[2] + y[3]);
+                        s1 += (y[4] + y[5]) + (y[6] + y[7]);
+                        sq = fmaf(y[0], y[0], fmaf(y[1], y[1], fmaf(y[2], y[2], fmaf(y[3], y[3], sq))));
+                        q1 = fmaf(y[4], y[4], fmaf(y[5], y[5], fmaf(y[6], y[6], fmaf(y[7], y[7], q1))));
+                        if (p.S > 0) {
+                            // tournament over the batch; ties keep the lower row (first occurrence, like max_pool2d)
+                            float c[8];
+                            int ix[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        if (r + u < rend) {
-                            s += y[u], sq = fmaf(y[u], y[u], sq);
-                            if (p.S > 0) {
-                                const int k = (r + u) & smask;
-                                const bool better = (k == 0) || (want_max ? (y[u] > best) : (y[u] < best));
-                                if (better) best = y[u], bi = k;
-                                if (k == smask) {
-                                    const long long g = (row0 + r + u) >> p.logS;
-                                    p.gsel[g * N + col] = best;
-                                    p.garg[g * N + col] = (uint8_t)bi;
+                            for (int u = 0; u < 8; ++u) c[u] = y[u] * sgn, ix[u] = u;
+#pragma unroll
+                            for (int w = 1; w < 8; w <<= 1)
+#pragma unroll
+                                for (int u = 0; u < 8; u += 2 * w) {
+                                    const bool gt = c[u + w] > c[u];
+                                    c[u] = gt ? c[u + w] : c[u];
+                                    ix[u] = gt ? ix[u + w] : ix[u];
                                 }
+                            const int k0 = r & smask;                 // position of this batch inside its group
+                            const bool take = (k0 == 0) || (c[0] > best);
+                            best = take ? c[0] : best;
+                            bi = take ? k0 + ix[0] : bi;
+                            if (((r + 8) & smask) == 0) {             // last batch of the group (warp-uniform)
+                                const long long g = (row0 + r) >> p.logS;
+                                p.gsel[g * N + col] = best * sgn;
+                                p.garg[g * N + col] = (uint8_t)bi;
+                            }
+                        }
+                    }
+                    s += s1, sq += q1;
+                } else {   // partial last tile or tiny groups: simple row loop
+                    const int rend = min(rbeg + rcnt, nvalid);
+                    float best = 0.f;
+                    int bi = 0;
+                    for (int r = rbeg; r < rend; ++r) {
+                        const float y = Cs[r * SM::kCStride + col];
+                        s += y, sq = fmaf(y, y, sq);
+                        if (p.S > 0) {
+                            const int k = r & smask;
+                            const bool better = (k == 0) || (want_max ? (y > best) : (y < best));
+                            best = better ? y : best;
+                            bi = better ? k : bi;
+                            if (k == smask) {
+                                const long long g = (row0 + r) >> p.logS;
+                                p.gsel[g * N + col] = best;
+                                p.garg[g * N + col] = (uint8_t)bi;
                             }
                         }
                     }
@@ -752,6 +789,7 @@ extern "C" int sg4d_linear_fwd(long long rows, int k, int lda, int n, int group,
     args.R = rows, args.wimg = wimg, args.Y = y, args.ldy = n, args.ycol0 = 0, args.partial = partial;
     args.S = group, args.logS = ilog2(group), args.gamma = gamma, args.gsel = gsel, args.garg = garg;
     const int grid = mlp_grid(rows);
+    args.dbg_no_tma = getenv("SG4D_DBG_NOTMA") != nullptr;
     return scale ? launch_row_n<1, 0>(n, args, grid, (cudaStream_t)stream)
                  : launch_row_n<0, 0>(n, args, grid, (cudaStream_t)stream);
 }
