@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) row_gemm_kernel(RowGemmArgs p)
         // Flat sequence of chunks q = (my tile index, k-block).  A static ring of PD register buffers keeps PD chunks
         // of loads in flight per thread (memory-level parallelism: 128 threads x PD x 8 x 16 B per SM), so the HBM
         // latency of one chunk is hidden behind the transform + MMA of the previous ones.
-        constexpr int PD = (PMODE <= 1) ? 4 : 3;
+        constexpr int PD = (PMODE <= 1) ? 4 : 2;      // modes 2/3 fetch two arrays per item: keep the ring within the register file
         const long long my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
         const long long total = my_tiles * nkb;
         RawVec buf[PD][kProdRows];
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) wgrad_kernel(WgradArgs p) {
         // Q slab: 32 rows x N channels = 8N float4.  Two k-blocks of loads are kept in flight per thread.
         constexpr int kQVec = N / 4;                    // float4 per Q row
         constexpr int kQItems = (32 * kQVec + kProdThreads - 1) / kProdThreads;
-        constexpr int PD = 2;                           // k-blocks of loads in flight per thread (register ring)
+        constexpr int PD = (N > 128) ? 1 : 2;           // k-blocks of loads in flight per thread (register ring, no spills)
         constexpr int kPItems = 32 * 32 / kProdThreads;   // float4 of the P slab per thread
         const int pc4 = tid & 31, pr0 = tid >> 5;       // P: my float4 column, rows pr0 + kProdWarps*i
         RawVec pv[PD][kPItems], qv[PD][kQItems];

@@ -27,3 +27,33 @@ if which == "fwd2":
 e1.record()
 torch.cuda.synchronize()
 print(which, rows, "ms", e0.elapsed_time(e1))
+
+if which in ("dw1", "da", "dw2"):
+    n1, n2, group, kp = 128, 128, 64, 196
+    G = rows // group
+    y1 = torch.randn(rows, n1, device=dev); y2 = torch.randn(rows, n2, device=dev); x = torch.randn(rows, kp, device=dev)
+    dz1 = torch.randn(rows, n1, device=dev)
+    p1, q1, u1 = torch.randn(n1, device=dev), torch.randn(n1, device=dev), torch.randn(n1, device=dev)
+    a2, b2 = torch.randn(n2, device=dev), torch.randn(n2, device=dev)
+    dsel = torch.randn(G, n2, device=dev); garg = torch.randint(0, group, (G, n2), device=dev, dtype=torch.uint8)
+    w2 = torch.randn(n2, n1, device=dev)
+    img = mlp.pack_weight(w2.t())
+    dw = torch.empty(n1, kp, device=dev); dw2 = torch.empty(n2, n1, device=dev)
+    part = torch.empty(_lib.load().sg4d_mlp_grid(rows) * 128 * 2, dtype=torch.float64, device=dev)
+    wp = mlp._wgrad_partial(rows, 224, dev)
+    def go():
+        if which == "dw1":
+            _lib.call("sg4d_inner_bwd_dw", x, rows, n1, kp, kp, y1.data_ptr(), dz1.data_ptr(), p1.data_ptr(), q1.data_ptr(),
+                      u1.data_ptr(), x.data_ptr(), wp.data_ptr(), dw.data_ptr())
+        elif which == "dw2":
+            _lib.call("sg4d_pool_bwd_dw", x, rows, n2, n1, group, y2.data_ptr(), a2.data_ptr(), b2.data_ptr(), dsel.data_ptr(),
+                      garg.data_ptr(), y1.data_ptr(), p1.data_ptr(), q1.data_ptr(), wp.data_ptr(), dw2.data_ptr())
+        else:
+            _lib.call("sg4d_pool_bwd_da", x, rows, n2, n1, group, y2.data_ptr(), a2.data_ptr(), b2.data_ptr(), dsel.data_ptr(),
+                      garg.data_ptr(), img.data_ptr(), y1.data_ptr(), p1.data_ptr(), q1.data_ptr(), p1.data_ptr(), u1.data_ptr(),
+                      dz1.data_ptr(), part.data_ptr())
+    for _ in range(3):
+        go()
+    torch.cuda.synchronize()
+    e0.record(); go(); e1.record(); torch.cuda.synchronize()
+    print(which, rows, "ms", e0.elapsed_time(e1))
