@@ -30,6 +30,9 @@ SIGNATURES = {
     "sg4d_ball_query_rows": [_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "sg4d_group_rows": [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
     "sg4d_group_rows_grad": [_i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "sg4d_spatial_index_build": [_i, _i, _i, _p, _p, _p],
+    "sg4d_fps_indexed": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "sg4d_ball_query_rows_indexed": [_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p],
     "sg4d_triplet_gather": [_i64, _i, _i, _p, _p, _p, _p, _p, _p],
     "sg4d_segment_sum": [_i, _i, _i64, _i, _i, _p, _i, _p, _p, _p, _p],
     "sg4d_pack_weight": [_i, _i, _i, _p, _p, _p],
@@ -42,7 +45,8 @@ SIGNATURES = {
     "sg4d_partial_sums": [_i, _i, _p, _p, _p],
 }
 OTHER_SYMBOLS = ["sg4d_abi_version", "sg4d_error_string", "sg4d_check_device", "sg4d_mlp_grid",
-                 "sg4d_weight_image_floats", "sg4d_wgrad_partial_floats"]
+                 "sg4d_weight_image_floats", "sg4d_wgrad_partial_floats", "sg4d_spatial_index_bytes",
+                 "sg4d_spatial_index_supported"]
 
 _lib = None
 
@@ -65,6 +69,8 @@ def load():
         lib.sg4d_mlp_grid.argtypes, lib.sg4d_mlp_grid.restype = [_i64], _i
         lib.sg4d_weight_image_floats.argtypes, lib.sg4d_weight_image_floats.restype = [_i, _i], _i64
         lib.sg4d_wgrad_partial_floats.argtypes, lib.sg4d_wgrad_partial_floats.restype = [_i64, _i], _i64
+        lib.sg4d_spatial_index_bytes.argtypes, lib.sg4d_spatial_index_bytes.restype = [_i, _i], _i64
+        lib.sg4d_spatial_index_supported.argtypes, lib.sg4d_spatial_index_supported.restype = [_i], _i
         if lib.sg4d_abi_version() != 1:
             raise RuntimeError("libsg4d.so ABI version mismatch; rebuild it")
         _lib = lib

@@ -28,7 +28,7 @@ struct BqScale {
 
 template <int NSC>
 __global__ void __launch_bounds__(kBqWarps * 32)
-ball_query_kernel(int n, int m, int pts_stride, int ctr_stride, int ctas_per_cloud,
+ball_query_kernel(int n, int n_scan, int m, int pts_stride, int ctr_stride, int ctas_per_cloud,
                   const float *__restrict__ centers, const float *__restrict__ pts, BqScale s0,
                   BqScale s1) {
     __shared__ float sx[kBqTile], sy[kBqTile], sz[kBqTile];
@@ -51,8 +51,8 @@ ball_query_kernel(int n, int m, int pts_stride, int ctr_stride, int ctas_per_clo
 
     bool done = !active;
     const unsigned lt = (1u << lane) - 1u;
-    for (int base = 0; base < n; base += kBqTile) {
-        const int tn = min(kBqTile, n - base);
+    for (int base = 0; base < n_scan; base += kBqTile) {   // n_scan < n: prefix pass, completed by spatial.cu
+        const int tn = min(kBqTile, n_scan - base);
         for (int i = tid; i < tn; i += kBqWarps * 32) {
             const float *r = pts + (size_t)(base + i) * pts_stride;
             sx[i] = __ldg(r), sy[i] = __ldg(r + 1), sz[i] = __ldg(r + 2);
@@ -97,7 +97,7 @@ ball_query_kernel(int n, int m, int pts_stride, int ctr_stride, int ctas_per_clo
     }
 }
 
-static int bq_launch(int b, int n, int m, int pts_stride, int ctr_stride, int nsc, const float *radius,
+int bq_launch(int b, int n, int n_scan, int m, int pts_stride, int ctr_stride, int nsc, const float *radius,
                      const int *nsample, const float *centers, const float *pts, int32_t *const *idx,
                      int32_t *const *cnt, cudaStream_t stream) {
     BqScale sc[2] = {{0.f, 0, nullptr, nullptr}, {0.f, 0, nullptr, nullptr}};
@@ -113,10 +113,10 @@ static int bq_launch(int b, int n, int m, int pts_stride, int ctr_stride, int ns
     const long long grid = (long long)b * cpc;
     if (grid > 0x7fffffffLL) return SG4D_EINVAL;
     if (nsc == 1)
-        ball_query_kernel<1><<<(unsigned)grid, kBqWarps * 32, 0, stream>>>(n, m, pts_stride, ctr_stride, cpc,
+        ball_query_kernel<1><<<(unsigned)grid, kBqWarps * 32, 0, stream>>>(n, n_scan, m, pts_stride, ctr_stride, cpc,
                                                                           centers, pts, sc[0], sc[1]);
     else
-        ball_query_kernel<2><<<(unsigned)grid, kBqWarps * 32, 0, stream>>>(n, m, pts_stride, ctr_stride, cpc,
+        ball_query_kernel<2><<<(unsigned)grid, kBqWarps * 32, 0, stream>>>(n, n_scan, m, pts_stride, ctr_stride, cpc,
                                                                           centers, pts, sc[0], sc[1]);
     return SG4D_LAUNCH_CHECK();
 }
@@ -128,7 +128,7 @@ extern "C" int sg4d_ball_query(int b, int n, int m, float radius, int nsample, c
     if (b < 0 || n <= 0 || m < 0 || nsample <= 0 || !new_xyz || !xyz || !idx) return SG4D_EINVAL;
     if (b == 0 || m == 0) return SG4D_OK;
     int32_t *idxs[1] = {idx};
-    return sg4d::bq_launch(b, n, m, 3, 3, 1, &radius, &nsample, new_xyz, xyz, idxs, nullptr,
+    return sg4d::bq_launch(b, n, n, m, 3, 3, 1, &radius, &nsample, new_xyz, xyz, idxs, nullptr,
                            (cudaStream_t)stream);
 }
 
@@ -142,7 +142,7 @@ extern "C" int sg4d_ball_query_rows(int b, int n, int m, int row_stride, int cen
     if (b == 0 || m == 0) return SG4D_OK;
     for (int s = 0; s < nscales; s += 2) {  // two radii per pass over the cloud
         const int k = nscales - s >= 2 ? 2 : 1;
-        const int st = sg4d::bq_launch(b, n, m, row_stride, center_stride, k, radius + s, nsample + s,
+        const int st = sg4d::bq_launch(b, n, n, m, row_stride, center_stride, k, radius + s, nsample + s,
                                        centers, pts, idx + s, cnt ? cnt + s : nullptr, (cudaStream_t)stream);
         if (st != SG4D_OK) return st;
     }

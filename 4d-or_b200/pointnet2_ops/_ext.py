@@ -9,7 +9,7 @@ chip; CPU tensors raise ``RuntimeError("CPU not supported")`` exactly like the r
 """
 import torch
 
-from .. import _lib
+from .. import _lib, rows
 
 _ONCHIP_MAX_POINTS = 16 * 1024 * 12  # fps.cu: 16-CTA cluster x 1024 threads x 12 points
 
@@ -27,6 +27,8 @@ def furthest_point_sampling(points, nsamples):
     _check(points, torch.float32, "points")
     _lib.require_cuda(points)
     b, n, _ = points.shape
+    if rows.wants_index(n):   # large clouds: bucket-pruned FPS on a spatial index (same picks, bit for bit)
+        return rows.fps_rows(points, nsamples, rows.SpatialIndex(points))[0]
     out = torch.empty(b, nsamples, dtype=torch.int32, device=points.device)
     tmp = torch.empty(b, n, dtype=torch.float32, device=points.device) if n > _ONCHIP_MAX_POINTS else None
     _lib.call("sg4d_furthest_point_sampling", points, b, n, nsamples, points.data_ptr(), _lib.ptr(tmp),
@@ -65,6 +67,8 @@ def ball_query(new_xyz, xyz, radius, nsample):
     _lib.require_cuda(new_xyz, xyz)
     b, n, _ = xyz.shape
     m = new_xyz.shape[1]
+    if rows.wants_index(n) and nsample <= 64:
+        return rows.ball_query_rows(new_xyz, xyz, [radius], [nsample], rows.SpatialIndex(xyz))[0][0]
     idx = torch.empty(b, m, nsample, dtype=torch.int32, device=xyz.device)
     _lib.call("sg4d_ball_query", xyz, b, n, m, float(radius), int(nsample), new_xyz.data_ptr(),
               xyz.data_ptr(), idx.data_ptr())

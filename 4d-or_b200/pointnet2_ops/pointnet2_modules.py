@@ -93,10 +93,14 @@ class _PointnetSAModuleBase(nn.Module):
                 outs.append(y.view(b, n, -1).amax(dim=1, keepdim=True))
             return None, torch.cat(outs, dim=2) if len(outs) > 1 else outs[0]
 
-        _, new_xyz = rows.fps_rows(pts, self.npoint)
+        # large clouds: one spatial index (Morton-sorted copy + bucket boxes) serves both FPS and the ball query
+        index = rows.SpatialIndex(pts) if rows.wants_index(n) else None
+        _, new_xyz = rows.fps_rows(pts, self.npoint, index)
         radii = [g.radius for g in self.groupers]
         nsamples = [g.nsample for g in self.groupers]
-        idx, cnt = rows.ball_query_rows(new_xyz, pts, radii, nsamples)
+        if index is not None and max(nsamples) > 64:
+            index = None
+        idx, cnt = rows.ball_query_rows(new_xyz, pts, radii, nsamples, index)
         for s, mlp in enumerate(self.mlps):
             assert self.groupers[s].use_xyz, "the hot path always groups xyz (use_xyz=True)"
             k = 3 + c

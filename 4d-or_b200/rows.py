@@ -9,6 +9,8 @@ import torch
 from . import _lib
 
 _ONCHIP_MAX_POINTS = 16 * 1024 * 12
+INDEX_MIN_POINTS = 12288    # clouds larger than this go through the spatial index (csrc/spatial.cu)
+BALL_QUERY_PREFIX = 4096    # points scanned by brute force before the index answers the remaining centres
 
 
 def _rows_ok(t, name):
@@ -17,24 +19,53 @@ def _rows_ok(t, name):
     _lib.require_cuda(t)
 
 
-def fps_rows(pts, npoint):
+class SpatialIndex:
+    """Device workspace holding the Morton-sorted copy + bucket boxes of a batch of clouds (include/sg4d.h)."""
+
+    def __init__(self, pts):
+        _rows_ok(pts, "pts")
+        b, n, s = pts.shape
+        lib = _lib.load()
+        if not lib.sg4d_spatial_index_supported(n):
+            raise RuntimeError(f"spatial index: unsupported cloud size n={n}")
+        self.b, self.n = b, n
+        self.ws = torch.empty(lib.sg4d_spatial_index_bytes(b, n) // 4, dtype=torch.float32, device=pts.device)
+        _lib.call("sg4d_spatial_index_build", pts, b, n, s, pts.data_ptr(), self.ws.data_ptr())
+        self.fps_consumed = False
+
+
+def wants_index(n, min_points=None):
+    """True when clouds of n points should go through the spatial index."""
+    lim = INDEX_MIN_POINTS if min_points is None else min_points
+    return n > lim and bool(_lib.load().sg4d_spatial_index_supported(n))
+
+
+def fps_rows(pts, npoint, index=None):
     """FPS + gather of the picked xyz.  pts (B,n,S) -> idx (B,npoint) int32, new_xyz (B,npoint,3).
     Replaces ``furthest_point_sample`` + ``gather_operation`` + transposes
-    (OPS/pointnet2_modules.py:50-59)."""
+    (OPS/pointnet2_modules.py:50-59).  With ``index`` (a fresh SpatialIndex of pts) the bucket-pruned
+    kernel runs; the result is bit-identical either way."""
     _rows_ok(pts, "pts")
     b, n, s = pts.shape
     idx = torch.empty(b, npoint, dtype=torch.int32, device=pts.device)
     new_xyz = torch.empty(b, npoint, 3, dtype=torch.float32, device=pts.device)
+    if index is not None:
+        if index.fps_consumed or (index.b, index.n) != (b, n):
+            raise RuntimeError("fps_rows needs a fresh SpatialIndex of the same clouds")
+        index.fps_consumed = True
+        _lib.call("sg4d_fps_indexed", pts, b, n, npoint, s, pts.data_ptr(), index.ws.data_ptr(), idx.data_ptr(),
+                  new_xyz.data_ptr())
+        return idx, new_xyz
     tmp = torch.empty(b, n, dtype=torch.float32, device=pts.device) if n > _ONCHIP_MAX_POINTS else None
     _lib.call("sg4d_fps_rows", pts, b, n, npoint, s, pts.data_ptr(), _lib.ptr(tmp), idx.data_ptr(),
               new_xyz.data_ptr())
     return idx, new_xyz
 
 
-def ball_query_rows(centers, pts, radii, nsamples):
+def ball_query_rows(centers, pts, radii, nsamples, index=None, prefix=None):
     """All radii of an MSG level in one scan.  centers (B,m,3|S'), pts (B,n,S) ->
     ([idx_s (B,m,ns_s) int32], [cnt_s (B,m) int32]).  Replaces one ``ball_query`` per scale
-    (OPS/pointnet2_utils.py:318)."""
+    (OPS/pointnet2_utils.py:318).  With ``index``: brute-force prefix + spatial index (same result)."""
     _rows_ok(pts, "pts")
     _rows_ok(centers, "centers")
     b, n, s = pts.shape
@@ -46,6 +77,14 @@ def ball_query_rows(centers, pts, radii, nsamples):
     ns_arr = (ctypes.c_int * k)(*[int(v) for v in nsamples])
     idx_arr = (ctypes.c_void_p * k)(*[t.data_ptr() for t in idx])
     cnt_arr = (ctypes.c_void_p * k)(*[t.data_ptr() for t in cnt])
+    if index is not None:
+        if (index.b, index.n) != (b, n):
+            raise RuntimeError("ball_query_rows: the SpatialIndex belongs to other clouds")
+        _lib.call("sg4d_ball_query_rows_indexed", pts, b, n, m, s, cs, k, ctypes.cast(r_arr, ctypes.c_void_p),
+                  ctypes.cast(ns_arr, ctypes.c_void_p), centers.data_ptr(), pts.data_ptr(), index.ws.data_ptr(),
+                  int(BALL_QUERY_PREFIX if prefix is None else prefix), ctypes.cast(idx_arr, ctypes.c_void_p),
+                  ctypes.cast(cnt_arr, ctypes.c_void_p))
+        return idx, cnt
     _lib.call("sg4d_ball_query_rows", pts, b, n, m, s, cs, k, ctypes.cast(r_arr, ctypes.c_void_p),
               ctypes.cast(ns_arr, ctypes.c_void_p), centers.data_ptr(), pts.data_ptr(),
               ctypes.cast(idx_arr, ctypes.c_void_p), ctypes.cast(cnt_arr, ctypes.c_void_p))

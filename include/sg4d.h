@@ -140,6 +140,26 @@ int sg4d_group_rows_grad(int b, int n, int m, int nsample, int c, int out_stride
                          const float *grad_out, const int32_t *idx, const int32_t *cnt,
                          float *grad_feats, sg4d_stream_t stream);
 
+/* ---- spatial index: exact acceleration of FPS and ball query on large clouds (csrc/spatial.cu) ----
+ * index = caller-provided device workspace of sg4d_spatial_index_bytes(b, n) bytes.  Build sorts every cloud into
+ * Morton-cell order (float4 {x, y, z, original index} + the FPS running minimum per point) and forms buckets of 64
+ * consecutive points with exact bounding boxes.  Supported for 1024 <= n <= 393216 (sg4d_spatial_index_supported). */
+long long sg4d_spatial_index_bytes(int b, int n);
+int sg4d_spatial_index_supported(int n);
+int sg4d_spatial_index_build(int b, int n, int row_stride, const float *pts, void *index, sg4d_stream_t stream);
+/* Same result as sg4d_fps_rows, bit for bit (same arithmetic, same tie-break); buckets whose bounding-box distance
+ * to the new pick is >= their largest running minimum are skipped.  Consumes the index's running minima: build the
+ * index again before another FPS call (the ball query below does not depend on them). */
+int sg4d_fps_indexed(int b, int n, int m, int row_stride, const float *pts, void *index, int32_t *idxs,
+                     float *new_xyz, sg4d_stream_t stream);
+/* Same result as sg4d_ball_query_rows, bit for bit.  prefix > 0: the first `prefix` points of every cloud are
+ * scanned by brute force with early exit (cheap for centres in dense regions) and only the centres still short of
+ * nsample hits are answered from the index; prefix == 0: index only.  cnt must be non-NULL when prefix > 0. */
+int sg4d_ball_query_rows_indexed(int b, int n, int m, int row_stride, int center_stride, int nscales,
+                                 const float *radius, const int *nsample, const float *centers, const float *pts,
+                                 const void *index, int prefix, int32_t *const *idx, int32_t *const *cnt,
+                                 sg4d_stream_t stream);
+
 /* TripletGCN message input (network_TripletGCN.py:45-46 + PyG __collect__):
  *   out[e, 0:d]      = x[dst[e]]      (x_i, edge_index[1])
  *   out[e, d:d+de]   = edge_feat[e]

@@ -148,6 +148,83 @@ def test_ball_query_rows_multi_radius(cuda, n, m, radii, nss, stride):
                 assert (np.diff(row[: c[bi, j]]) > 0).all() and (row[c[bi, j]:] == row[0]).all()
 
 
+# ------------------------------------------------------------------ spatial index (csrc/spatial.cu)
+
+def _bench_like_clouds(seed, b, n, stride):
+    """the benchmark's own cloud generator (Gaussian mixture on the unit sphere, duplicates, zero rows)"""
+    from sg4d import synthetic
+    g = torch.Generator().manual_seed(seed)
+    return torch.stack([synthetic.make_cloud(g, n, stride) for _ in range(b)])
+
+
+@pytest.mark.parametrize("stride,n,m,kind", [(3, 1024, 128, "mixed"), (6, 1500, 200, "mixed"), (7, 4000, 512, "mixed"),
+                                             (6, 8191, 512, "mixed"), (7, 20000, 512, "bench"), (6, 80000, 512, "bench"),
+                                             (7, 80000, 512, "mixed"), (3, 200001, 64, "mixed")])
+def test_fps_indexed_bit_exact(cuda, stride, n, m, kind):
+    """bucket-pruned FPS == the oracle's literal simulation of the reference kernel (ties, skip rule, padding)"""
+    from sg4d import rows
+    b = 4 if n <= 20000 else 2
+    if kind == "bench":
+        pts = _bench_like_clouds(n + stride, b, n, stride)
+    else:
+        pts = torch.rand(b, n, stride, generator=torch.Generator().manual_seed(n))
+        pts[:, :, :3] = _clouds(n + 3, b, n)
+    want = ora.furthest_point_sampling(pts[:, :, :3].contiguous(), m)
+    dpts = pts.to(cuda)
+    idx, new_xyz = rows.fps_rows(dpts, m, rows.SpatialIndex(dpts))
+    np.testing.assert_array_equal(idx.cpu().numpy(), want.numpy())
+    picked = torch.gather(pts[:, :, :3], 1, want.long().unsqueeze(-1).expand(-1, -1, 3))
+    assert torch.equal(new_xyz.cpu(), picked)
+    idx2, _ = rows.fps_rows(dpts, m, rows.SpatialIndex(dpts))       # the bucket layout depends on atomics; the picks do not
+    assert torch.equal(idx, idx2)
+
+
+def test_fps_indexed_degenerate_clouds(cuda):
+    from sg4d import rows
+    n, m = 2048, 40
+    pts = torch.rand(5, n, 3, generator=torch.Generator().manual_seed(9))
+    pts[0] *= 0.01                          # everything skipped by the |p|^2 <= 1e-3 rule: all picks are index 0
+    pts[1] = pts[1, :1]                     # one point repeated: all distances tie at 0 after the first pick
+    pts[2, :, 1:] = 0.25                    # collinear
+    pts[3, 5:] = 0.0                        # five candidates, the rest skipped
+    pts[4, 100] = float("nan")              # a NaN point keeps temp = 1e10 forever in the reference
+    want = ora.furthest_point_sampling(pts, m)
+    got, _ = rows.fps_rows(pts.to(cuda), m, rows.SpatialIndex(pts.to(cuda)))
+    np.testing.assert_array_equal(got.cpu().numpy(), want.numpy())
+
+
+@pytest.mark.parametrize("n,m,radii,nss,stride,prefix,kind", [
+    (1024, 128, [0.2, 0.4], [32, 64], 3, 0, "mixed"), (4000, 512, [0.1, 0.2], [16, 32], 6, 0, "mixed"),
+    (4000, 512, [0.1, 0.2], [16, 32], 7, 512, "mixed"), (20000, 512, [0.1, 0.2], [16, 32], 7, 4096, "bench"),
+    (20000, 200, [0.5], [64], 6, 0, "bench"), (80000, 512, [0.1, 0.2], [16, 32], 7, 4096, "bench"),
+    (80000, 512, [0.1, 0.2], [16, 32], 6, 0, "bench"), (30000, 64, [0.05, 0.1, 0.3], [4, 8, 16], 6, 1000, "mixed")])
+def test_ball_query_indexed_bit_exact(cuda, n, m, radii, nss, stride, prefix, kind):
+    """prefix scan + spatial index == the oracle's serial scan (first nsample hits in index order, first-hit fill,
+    zero rows), including dense balls with thousands of hits (buffer compaction) and prefix = 0 (index only)"""
+    from sg4d import rows
+    b = 2
+    if kind == "bench":
+        pts = _bench_like_clouds(n + stride + prefix, b, n, stride)
+    else:
+        pts = torch.rand(b, n, stride, generator=torch.Generator().manual_seed(n))
+        pts[:, :, :3] = _clouds(n + 11, b, n)
+    xyz = pts[:, :, :3].contiguous()
+    fps = ora.furthest_point_sampling(xyz, m)
+    new_xyz = ora.gather_points(xyz.transpose(1, 2).contiguous(), fps).transpose(1, 2).contiguous()
+    new_xyz[0, -1] = 7.0                   # a centre without any neighbour: the row stays zero
+    dpts = pts.to(cuda)
+    idx, cnt = rows.ball_query_rows(new_xyz.to(cuda), dpts, radii, nss, rows.SpatialIndex(dpts), prefix=prefix)
+    for s, (r, ns) in enumerate(zip(radii, nss)):
+        want = ora.ball_query(new_xyz, xyz, r, ns)
+        np.testing.assert_array_equal(idx[s].cpu().numpy(), want.numpy())
+        w = want.numpy()
+        distinct = np.array([[len(set(row.tolist())) for row in cl] for cl in w])
+        got_cnt = cnt[s].cpu().numpy()
+        nohit = (new_xyz.numpy()[:, :, 0] == 7.0)
+        np.testing.assert_array_equal(got_cnt[~nohit], distinct[~nohit])
+        assert (got_cnt[nohit] == 0).all()
+
+
 @pytest.mark.parametrize("c,feat_stride,feat_off,n,m,ns", [(3, 6, 3, 2048, 512, 16), (4, 7, 3, 2048, 512, 32),
                                                            (192, 192, 0, 512, 128, 64), (5, 5, 0, 300, 20, 8)])
 def test_group_rows_forward_backward(cuda, c, feat_stride, feat_off, n, m, ns):
