@@ -283,16 +283,17 @@ struct FpsBucketOut {
     unsigned slot;
 };
 
-__global__ void __launch_bounds__(kFpsThreads)
+__global__ void __launch_bounds__(1024)
 fps_indexed_kernel(int n, int m, int row_stride, int L, const float *__restrict__ pts, float *__restrict__ ws,
                    long long ws_words, int32_t *__restrict__ idxs, float *__restrict__ new_xyz) {
     extern __shared__ float s_dyn[];
     __shared__ int s_nact;
-    __shared__ int s_wbest[kFpsWarps];
-    __shared__ unsigned s_wmin[kFpsWarps], s_wmax[kFpsWarps];
-    __shared__ unsigned s_tie_pr[kFpsWarps];
+    __shared__ int s_wbest[32];
+    __shared__ unsigned s_wmin[32], s_wmax[32];
+    __shared__ unsigned s_tie_pr[32];
     __shared__ int s_tie_bucket;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int kFpsThreads = blockDim.x, kFpsWarps = kFpsThreads >> 5;   // 256 .. 1024 threads: more per cloud when clouds are few
     const unsigned lt = (1u << lane) - 1u;
     const IndexLayout lay = index_layout(n);
     const int nb = lay.nb, nbp = (nb + 31) / 32 * 32;
@@ -621,7 +622,9 @@ extern "C" int sg4d_fps_indexed(int b, int n, int m, int row_stride, const float
     const size_t smem = (size_t)nbp * (8 * 4 + 2);
     cudaError_t e = cudaFuncSetAttribute(fps_indexed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return status_of(e);
-    fps_indexed_kernel<<<b, kFpsThreads, smem, (cudaStream_t)stream>>>(n, m, row_stride, L, pts, (float *)index,
+    // one CTA per cloud; with few clouds a CTA gets more warps (the early rounds touch every bucket)
+    const int threads = b <= 160 ? 1024 : (b <= 320 ? 512 : kFpsThreads);
+    fps_indexed_kernel<<<b, threads, smem, (cudaStream_t)stream>>>(n, m, row_stride, L, pts, (float *)index,
                                                                       ws_words_of(n), idxs, new_xyz);
     return SG4D_LAUNCH_CHECK();
 }

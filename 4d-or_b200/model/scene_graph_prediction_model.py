@@ -63,9 +63,29 @@ class SGPNModelWrapper(nn.Module):
             n_object_types=self.n_object_types)
 
     # ------------------------------------------------------------------ forward (reference :87-109)
+    # the two encoders are independent until the GCN: the (small) object encoder runs on a side stream so that
+    # its latency-bound kernels (12 clouds per scene) share the GPU with the edge encoder's (66 clouds per scene)
+    overlap_encoders = True
+
+    def _encode(self, batch):
+        obj_points, rel_points = batch['obj_points'], batch['rel_points']
+        if not (self.overlap_encoders and obj_points.is_cuda):
+            return self.obj_encoder(obj_points), self.rel_encoder(rel_points)
+        main = torch.cuda.current_stream(obj_points.device)
+        side = self.__dict__.get('_side_stream')
+        if side is None or side.device != obj_points.device:
+            side = torch.cuda.Stream(device=obj_points.device)
+            self.__dict__['_side_stream'] = side
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            obj_feature = self.obj_encoder(obj_points)
+        rel_feature = self.rel_encoder(rel_points)
+        main.wait_stream(side)
+        obj_feature.record_stream(main)
+        return obj_feature, rel_feature
+
     def forward(self, batch, return_meta_data=False):
-        obj_feature = self.obj_encoder(batch['obj_points'])
-        rel_feature = self.rel_encoder(batch['rel_points'])
+        obj_feature, rel_feature = self._encode(batch)
         gcn_obj_feature, gcn_rel_feature = self.gcn(obj_feature, rel_feature, batch['edge_indices'])
 
         obj_cls = self.obj_predictor(gcn_obj_feature if self.mconfig['OBJ_PRED_FROM_GCN'] else obj_feature)

@@ -61,3 +61,71 @@ class GradBucket:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             self.flat.div_(dist.get_world_size())
         return self.flat
+
+
+class DevicePrefetcher:
+    """Double-buffered host -> device staging of batch dicts on a side stream, so that the upload of batch i+1
+    overlaps the compute of batch i (the reference relies on Lightning's synchronous ``batch_to_device``).
+
+        pf = DevicePrefetcher(device)
+        pf.submit(host_batch)                 # pinned host tensors
+        for ...:
+            batch = pf.next()                 # device tensors; the current stream waits for their copy
+            pf.submit(next_host_batch)        # starts copying while the step below runs
+            step(batch)
+
+    Point tensors ``*_points`` keep the (B, N, C) row layout underneath their (B, C, N) view, like
+    ``synthetic.to_device``.  Two sets of device buffers are reused round-robin; a buffer is only overwritten
+    after the compute stream has passed the ``next()`` that follows its last use.
+    """
+
+    def __init__(self, device, depth=2):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.slots = [dict(buf={}, ready=None, free=None) for _ in range(depth)]
+        self.head = self.tail = 0
+        self.pending = 0
+
+    @staticmethod
+    def _base(k, v):
+        return v.permute(0, 2, 1) if (v.dim() == 3 and k.endswith("_points")) else v
+
+    def submit(self, host_batch):
+        if self.pending == len(self.slots):
+            raise RuntimeError("DevicePrefetcher: all buffers are in flight; call next() first")
+        slot = self.slots[self.head]
+        self.head = (self.head + 1) % len(self.slots)
+        self.pending += 1
+        out = {}
+        with torch.cuda.stream(self.stream):
+            if slot["free"] is not None:
+                self.stream.wait_event(slot["free"])      # the compute stream is done with this buffer
+            for k, v in host_batch.items():
+                if not torch.is_tensor(v):
+                    out[k] = v
+                    continue
+                src = self._base(k, v)
+                dst = slot["buf"].get(k)
+                if dst is None or dst.shape != src.shape or dst.dtype != src.dtype:
+                    dst = torch.empty(src.shape, dtype=src.dtype, device=self.device)
+                    slot["buf"][k] = dst
+                dst.copy_(src, non_blocking=True)
+                out[k] = self._base(k, dst)
+            slot["ready"] = torch.cuda.Event()
+            slot["ready"].record(self.stream)
+        slot["out"] = out
+
+    def next(self):
+        if self.pending == 0:
+            raise RuntimeError("DevicePrefetcher: nothing submitted")
+        prev = self.slots[(self.tail - 1) % len(self.slots)]
+        cur = torch.cuda.current_stream(self.device)
+        if prev.get("out") is not None:
+            # everything enqueued so far on the compute stream (the previous step) precedes the reuse of its buffer
+            prev["free"] = torch.cuda.Event()
+            prev["free"].record(cur)
+        slot = self.slots[self.tail]
+        self.tail = (self.tail + 1) % len(self.slots)
+        self.pending -= 1
+        cur.wait_event(slot["ready"])
+        return slot["out"]
