@@ -36,10 +36,15 @@ namespace sg4d {
 constexpr int kTileM = 128;       // rows per tile = UMMA M
 constexpr int kKB = 32;           // fp32 per k-block (one 128-byte swizzle row)
 constexpr int kStages = 2;
+// T1 (row_gemm): warps 0-7 producers, 8 MMA, 9-12 epilogue (kEpiThreads = 256 -- two warps per TMEM lane quarter --
+// is supported by the code below but measured slower: the register cap drops to 96 and the producers spill).
 constexpr int kProdThreads = 256, kEpiThreads = 128;
 constexpr int kProdWarps = kProdThreads / 32;
 constexpr int kProdRows = kTileM * 8 / kProdThreads;          // float4 items per producer thread per T1 k-block
-constexpr int kMlpThreads = kProdThreads + 32 + kEpiThreads;   // warps 0-7 producers, 8 MMA, 9-12 epilogue
+constexpr int kMlpThreads = kProdThreads + 32 + kEpiThreads;
+// T2 (wgrad): no per-tile epilogue; the operand transform bounds it, hence 16 producer warps (+1 MMA, +4 epilogue)
+constexpr int kProdThreadsT2 = 512;
+constexpr int kMlpThreadsT2 = kProdThreadsT2 + 32 + 128;
 
 // ------------------------------------------------------------------------------------------------
 // Operand generator: element (row, col) of the logical operand matrix P, computed from arrays in HBM.
@@ -104,16 +109,23 @@ __device__ __forceinline__ float4 op_apply(const Operand &o, const RawVec &r, lo
 
 // One lane polls the mbarrier, the rest of the warp waits at the warp barrier: 32x fewer try_wait requests hit
 // the barrier unit (with every thread polling, the waits themselves were the top stall in the first ncu capture).
+// SLEEP_NS > 0: back off between polls.  The waiting warps share the four issue ports with the producers, and the
+// ncu instruction counts showed ~45 % of all issued instructions to be try_wait / branch / yield of such loops.
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait_warp(int lane, uint32_t bar, uint32_t parity) {
-    if (lane == 0) tc::mbar_wait(bar, parity);
+    if (lane == 0) {
+        while (!tc::mbar_try_wait(bar, parity)) {
+            if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+        }
+    }
     __syncwarp();
 }
 
 __device__ __forceinline__ void split4(const float4 &v, float4 &hi, float4 &lo) {
-    tc::split_tf32(v.x, hi.x, lo.x);
-    tc::split_tf32(v.y, hi.y, lo.y);
-    tc::split_tf32(v.z, hi.z, lo.z);
-    tc::split_tf32(v.w, hi.w, lo.w);
+    tc::split_tf32_fast(v.x, hi.x, lo.x);
+    tc::split_tf32_fast(v.y, hi.y, lo.y);
+    tc::split_tf32_fast(v.z, hi.z, lo.z);
+    tc::split_tf32_fast(v.w, hi.w, lo.w);
 }
 
 // ================================================================================================
@@ -134,7 +146,7 @@ struct RowGemmArgs {
     uint8_t *garg;           // (R/S, N)
     const float *E;          // EMODE 1: (R, N) pre-activation of the layer whose ReLU is differentiated
     const float *es, *et, *ei, *em;   // (N) each
-    int dbg_no_tma;
+    int dbg_no_tma, dbg_no_mma, dbg_no_load;
 };
 
 template <int N>
@@ -174,7 +186,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) row_gemm_kernel(RowGemmArgs p)
         }
         for (int a = 0; a < 2; ++a) {
             tc::mbar_init(bar_tfull + 8 * a, 1);
-            tc::mbar_init(bar_tempty + 8 * a, 4);
+            tc::mbar_init(bar_tempty + 8 * a, kEpiThreads / 32);
         }
         tc::mbar_fence_init();
     }
@@ -202,7 +214,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) row_gemm_kernel(RowGemmArgs p)
         const long long total = my_tiles * nkb;
         RawVec buf[PD][kProdRows];
         auto issue = [&](long long q, RawVec (&dst)[kProdRows]) {
-            if (q < total) {
+            if (q < total && !p.dbg_no_load) {
                 const long long tile = blockIdx.x + (q / nkb) * gridDim.x;
                 const int kb = (int)(q % nkb);
 #pragma unroll
@@ -252,18 +264,18 @@ __global__ void __launch_bounds__(kMlpThreads, 1) row_gemm_kernel(RowGemmArgs p)
         long long it = 0, ti = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
             const int acc = (int)(ti & 1);
-            mbar_wait_warp(lane, bar_tempty + 8 * acc, (uint32_t)(((ti >> 1) & 1) ^ 1));
+            mbar_wait_warp<32>(lane, bar_tempty + 8 * acc, (uint32_t)(((ti >> 1) & 1) ^ 1));
             tc::tc_fence_after_sync();
             const uint32_t d_tmem = tmem + (uint32_t)(acc * N);
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int stage = (int)(it % kStages);
-                mbar_wait_warp(lane, bar_full + 8 * stage, (uint32_t)((it / kStages) & 1));
+                mbar_wait_warp<20>(lane, bar_full + 8 * stage, (uint32_t)((it / kStages) & 1));
                 tc::tc_fence_after_sync();
                 if (lane == 0) {
                     const uint32_t a_hi = smem_base + stage * SM::kStageBytes, a_lo = a_hi + SM::kABytes;
                     const uint32_t w_hi = a_hi + 2 * SM::kABytes, w_lo = w_hi + SM::kWBytes;
 #pragma unroll
-                    for (int ks = 0; ks < kKB / 8; ++ks) {
+                    for (int ks = 0; ks < kKB / 8 && !p.dbg_no_mma; ++ks) {
                         const uint64_t dah = tc::umma_desc_k_sw128(a_hi + ks * 32), dal = tc::umma_desc_k_sw128(a_lo + ks * 32);
                         const uint64_t dwh = tc::umma_desc_k_sw128(w_hi + ks * 32), dwl = tc::umma_desc_k_sw128(w_lo + ks * 32);
                         tc::umma_tf32(d_tmem, dal, dwh, idesc, (kb | ks) != 0);   // small terms first
@@ -278,23 +290,26 @@ __global__ void __launch_bounds__(kMlpThreads, 1) row_gemm_kernel(RowGemmArgs p)
         }
     } else {
         // =============================================================== epilogue
-        const int e = tid - (kProdThreads + 32);   // 0..127
+        const int e = tid - (kProdThreads + 32);   // 0..255
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
+        const int half = e >> 7;                   // which half of the 32-column chunks this warp moves
         const int row = q * 32 + lane;             // my accumulator row
-        // column-owner mapping for the statistics / group pass
-        const int col = (N == 128) ? e : (e & (N - 1));
-        const int rbeg = (N == 128) ? 0 : (e / N) * (kTileM / (kEpiThreads / N));
-        const int rcnt = (N == 128) ? kTileM : kTileM / (kEpiThreads / N);
+        // column-owner mapping for the statistics / group pass: N = 128 -> 2 threads per column (64 rows each),
+        // N = 64 -> 4 threads per column (32 rows each); a max-pool group never straddles two owners
+        const int col = e & (N - 1);
+        const int rbeg = (e / N) * (kTileM / (kEpiThreads / N));
+        const int rcnt = kTileM / (kEpiThreads / N);
         bool want_max = true;
         if (EMODE == 0 && p.S > 0) want_max = __ldg(p.gamma + col) >= 0.f;
         double dacc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         long long ti = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
             const int acc = (int)(ti & 1);
-            mbar_wait_warp(lane, bar_tfull + 8 * acc, (uint32_t)((ti >> 1) & 1));
+            mbar_wait_warp<128>(lane, bar_tfull + 8 * acc, (uint32_t)((ti >> 1) & 1));
             tc::tc_fence_after_sync();
 #pragma unroll
-            for (int ch = 0; ch < N / 32; ++ch) {
+            for (int c2 = 0; c2 < N / 32 / (kEpiThreads / 128); ++c2) {
+                const int ch = (kEpiThreads / 128) * c2 + half;
                 uint32_t v[32];
                 tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N + ch * 32), v);
                 tc::tmem_ld_wait();
@@ -457,6 +472,7 @@ struct WgradArgs {
     long long R;
     float *partial;          // (gridDim.x, 128, N)
     uint32_t d_lbo, d_sbo, d_type, d_kstep;   // MN-major descriptor fields (bytes / layout type)
+    int dbg_no_mma, dbg_no_load;
 };
 
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t type) {
@@ -487,7 +503,8 @@ struct WgSmem {
 };
 
 template <int N, int PMODE, int QMODE>
-__global__ void __launch_bounds__(kMlpThreads, 1) wgrad_kernel(WgradArgs p) {
+__global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
+    constexpr int kProdThreads = kProdThreadsT2, kProdWarps = kProdThreads / 32, kMlpThreads = kMlpThreadsT2;
     using SM = WgSmem<N>;
     constexpr int kTmemCols = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
     extern __shared__ uint8_t smem_raw[];
@@ -538,7 +555,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) wgrad_kernel(WgradArgs p) {
         const int pc4 = tid & 31, pr0 = tid >> 5;       // P: my float4 column, rows pr0 + kProdWarps*i
         RawVec pv[PD][kPItems], qv[PD][kQItems];
         auto issue = [&](long long kbk, RawVec (&pd)[kPItems], RawVec (&qd)[kQItems]) {
-            if (kbk < nkb_total) {
+            if (kbk < nkb_total && !p.dbg_no_load) {
                 const long long row_base = t_beg * kTileM + kbk * kKB;
 #pragma unroll
                 for (int i = 0; i < kPItems; ++i) op_load<PMODE>(p.P, row_base + pr0 + kProdWarps * i, p.R, 4 * pc4, pd[i]);
@@ -596,13 +613,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) wgrad_kernel(WgradArgs p) {
         constexpr uint32_t idesc = tc::umma_idesc_tf32(kTileM, N) | (1u << 15) | (1u << 16);
         for (long long kbk = 0; kbk < nkb_total; ++kbk) {
             const int stage = (int)(kbk % kStages);
-            mbar_wait_warp(lane, bar_full + 8 * stage, (uint32_t)((kbk / kStages) & 1));
+            mbar_wait_warp<20>(lane, bar_full + 8 * stage, (uint32_t)((kbk / kStages) & 1));
             tc::tc_fence_after_sync();
             if (lane == 0) {
                 const uint32_t p_hi = smem_base + stage * SM::kStageBytes, p_lo = p_hi + SM::kPBytes;
                 const uint32_t q_hi = p_hi + 2 * SM::kPBytes, q_lo = q_hi + SM::kQBytes;
 #pragma unroll
-                for (int ks = 0; ks < kKB / 8; ++ks) {   // 8 rows = one 1024-byte atom per chunk
+                for (int ks = 0; ks < kKB / 8 && !p.dbg_no_mma; ++ks) {   // 8 rows = one 1024-byte atom per chunk
                     const uint32_t ko = ks * p.d_kstep;
                     const uint64_t dph = umma_desc_mn(p_hi + ko, p.d_lbo, p.d_sbo, p.d_type), dpl = umma_desc_mn(p_lo + ko, p.d_lbo, p.d_sbo, p.d_type);
                     const uint64_t dqh = umma_desc_mn(q_hi + ko, p.d_lbo, p.d_sbo, p.d_type), dql = umma_desc_mn(q_lo + ko, p.d_lbo, p.d_sbo, p.d_type);
@@ -620,7 +637,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) wgrad_kernel(WgradArgs p) {
         const int q = warp & 3, row = q * 32 + lane;
         float *out = p.partial + ((size_t)blockIdx.x * kTileM + row) * N;
         if (nkb_total > 0) {
-            mbar_wait_warp(lane, bar_done, 0u);
+            mbar_wait_warp<2000>(lane, bar_done, 0u);
             tc::tc_fence_after_sync();
 #pragma unroll
             for (int ch = 0; ch < N / 32; ++ch) {
@@ -709,7 +726,9 @@ __global__ void partial_sum_kernel(int N, int nparts, const double *__restrict__
 }
 
 template <int N, int PM, int EM>
-static int launch_row(const RowGemmArgs &a, int grid, cudaStream_t stream) {
+static int launch_row(const RowGemmArgs &a0, int grid, cudaStream_t stream) {
+    RowGemmArgs a = a0;
+    a.dbg_no_mma = getenv("SG4D_DBG_NOMMA") != nullptr, a.dbg_no_load = getenv("SG4D_DBG_NOLOAD") != nullptr;
     auto kern = row_gemm_kernel<N, PM, EM>;
     const int smem = RowSmem<N>::kTotal;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -724,12 +743,14 @@ static int launch_row_n(int n, const RowGemmArgs &a, int grid, cudaStream_t stre
 }
 
 template <int N, int PM, int QM>
-static int launch_wgrad(const WgradArgs &a, int grid, cudaStream_t stream) {
+static int launch_wgrad(const WgradArgs &a0, int grid, cudaStream_t stream) {
+    WgradArgs a = a0;
+    a.dbg_no_mma = getenv("SG4D_DBG_NOMMA") != nullptr, a.dbg_no_load = getenv("SG4D_DBG_NOLOAD") != nullptr;
     auto kern = wgrad_kernel<N, PM, QM>;
     const int smem = WgSmem<N>::kTotal;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return status_of(e);
-    kern<<<grid, kMlpThreads, smem, stream>>>(a);
+    kern<<<grid, kMlpThreadsT2, smem, stream>>>(a);
     return SG4D_LAUNCH_CHECK();
 }
 
@@ -754,6 +775,7 @@ static int mlp_grid(long long rows) {
 using namespace sg4d;
 
 extern "C" int sg4d_mlp_grid(long long rows) { return mlp_grid(rows); }
+extern "C" long long sg4d_mlp_partial_doubles(long long rows) { return (long long)mlp_grid(rows) * kEpiThreads * 2; }
 
 extern "C" long long sg4d_weight_image_floats(int n, int k) {
     return (long long)((k + kKB - 1) / kKB) * 2 * n * kKB;
@@ -781,8 +803,8 @@ extern "C" int sg4d_linear_fwd(long long rows, int k, int lda, int n, int group,
                                const float *shift, const float *wimg, float *y, double *partial, const float *gamma,
                                float *gsel, uint8_t *garg, sg4d_stream_t stream) {
     if (!row_common_ok(rows, k, lda, n) || !a || !wimg || !partial || (scale && !shift)) return SG4D_EINVAL;
-    if (group != 0 && (group < 1 || group > 128 || (128 % group) || (n == 64 && group > 64) || rows % group || !gamma ||
-                       !gsel || !garg))
+    if (group != 0 && (group < 1 || (128 % group) || group > kTileM / (kEpiThreads / n) || rows % group || !gamma || !gsel ||
+                       !garg))
         return SG4D_EINVAL;
     RowGemmArgs args{};
     args.op.A = a, args.op.lda = lda, args.op.s = scale, args.op.t = shift, args.op.ncols = k;

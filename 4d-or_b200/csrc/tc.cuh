@@ -131,5 +131,15 @@ __device__ __forceinline__ void split_tf32(float a, float &hi, float &lo) {
     lo = __uint_as_float(h);  // |a - hi - lo| <= 2^-22 |a|, unbiased
 }
 
+// Same contract in 3 instructions instead of 9 (cvt.rna.tf32 compiles to add / isfinite / select / mask on sm_100):
+// hi = a with the 13 low mantissa bits cleared (what the tensor core would read anyway), r = a - hi exact with
+// |r| < 2^-10 |a|, lo = r rounded to nearest by adding half an ulp of tf32 before the hardware truncates it
+// (r is tiny, so the add cannot overflow the exponent).  |a - hi - lo| <= 2^-21 |a|, unbiased.
+__device__ __forceinline__ void split_tf32_fast(float a, float &hi, float &lo) {
+    hi = __uint_as_float(__float_as_uint(a) & 0xffffe000u);
+    const float r = a - hi;
+    lo = __uint_as_float(__float_as_uint(r) + 0x1000u);
+}
+
 }  // namespace tc
 }  // namespace sg4d

@@ -34,8 +34,7 @@ def linear_fwd(a, k, wimg, n, scale=None, shift=None, group=0, gamma=None, store
     rows, lda = a.shape
     dev = a.device
     y = torch.empty(rows, n, dtype=torch.float32, device=dev) if store_y else None
-    grid = _lib.load().sg4d_mlp_grid(rows)
-    partial = torch.empty(grid * 128 * 2, dtype=torch.float64, device=dev)
+    partial = torch.empty(_lib.load().sg4d_mlp_partial_doubles(rows), dtype=torch.float64, device=dev)
     gsel = garg = None
     if group:
         gsel = torch.empty(rows // group, n, dtype=torch.float32, device=dev)
@@ -129,7 +128,7 @@ class _FusedSharedMLP(torch.autograd.Function):
         dsel = (dz * s2).contiguous()
         em1 = (-m1 * i1).contiguous()
         dz1 = torch.empty(rows, n1, dtype=torch.float32, device=dev)
-        part = torch.empty(_lib.load().sg4d_mlp_grid(rows) * 128 * 2, dtype=torch.float64, device=dev)
+        part = torch.empty(_lib.load().sg4d_mlp_partial_doubles(rows), dtype=torch.float64, device=dev)
         _lib.call("sg4d_pool_bwd_da", x, rows, n2, n1, group, y2.data_ptr(), a2.data_ptr(), b2.data_ptr(), dsel.data_ptr(),
                   garg.data_ptr(), pack_weight(w2.t()).data_ptr(), y1.data_ptr(), s1.data_ptr(), t1.data_ptr(),
                   i1.data_ptr(), em1.data_ptr(), dz1.data_ptr(), part.data_ptr())

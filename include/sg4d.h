@@ -189,16 +189,18 @@ int sg4d_segment_sum(int n_nodes, int d, int64_t src_stride, int col0, int col1,
  * need: per-channel sum / sum of squares and, optionally, the per-group extreme pre-activation.
  * ---------------------------------------------------------------------------------------------- */
 
-/* number of CTAs sg4d_linear_fwd launches for `rows` rows (= leading dimension of `partial`) */
+/* number of CTAs sg4d_linear_fwd launches for `rows` rows */
 int sg4d_mlp_grid(long long rows);
+/* size (in doubles) of the `partial` statistics buffer of sg4d_linear_fwd / sg4d_pool_bwd_da for `rows` rows */
+long long sg4d_mlp_partial_doubles(long long rows);
 /* size (in floats) of the packed image of an (n, k) weight */
 long long sg4d_weight_image_floats(int n, int k);
 /* w (n, k) fp32, row stride ldw  ->  img: per 32-column k-block, the TF32 hi and lo parts as 128-byte
  * swizzled K-major tiles (the exact shared-memory image the MMA reads; loaded by one bulk-TMA copy) */
 int sg4d_pack_weight(int n, int k, int ldw, const float *w, float *img, sg4d_stream_t stream);
 /* a (rows, lda) fp32, k valid columns (k % 4 == 0, k <= 256); scale/shift (k) or NULL (identity, no ReLU);
- * n in {64, 128}; y (rows, n) or NULL; partial (sg4d_mlp_grid(rows), 128, 2) fp64 sums for
- * sg4d_bn_finalize; group = nsample for the fused max-pool (0 = none; must divide 128 and rows):
+ * n in {64, 128}; y (rows, n) or NULL; partial: sg4d_mlp_partial_doubles(rows) fp64 sums for
+ * sg4d_bn_finalize; group = nsample for the fused max-pool (0 = none; a power of two dividing rows; <= 128 for n = 128, <= 64 for n = 64):
  * gsel (rows/group, n) = max (gamma[c] >= 0) or min (gamma[c] < 0) of y over the group, garg = its row. */
 int sg4d_linear_fwd(long long rows, int k, int lda, int n, int group, const float *a, const float *scale,
                     const float *shift, const float *wimg, float *y, double *partial, const float *gamma,

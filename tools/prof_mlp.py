@@ -39,7 +39,7 @@ if which in ("dw1", "da", "dw2"):
     w2 = torch.randn(n2, n1, device=dev)
     img = mlp.pack_weight(w2.t())
     dw = torch.empty(n1, kp, device=dev); dw2 = torch.empty(n2, n1, device=dev)
-    part = torch.empty(_lib.load().sg4d_mlp_grid(rows) * 128 * 2, dtype=torch.float64, device=dev)
+    part = torch.empty(_lib.load().sg4d_mlp_partial_doubles(rows), dtype=torch.float64, device=dev)
     wp = mlp._wgrad_partial(rows, 224, dev)
     def go():
         if which == "dw1":
