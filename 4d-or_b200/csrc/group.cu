@@ -129,6 +129,50 @@ group_rows_wide_kernel(long long rows, int n, int m, int nsample, int c, int pts
     }
 }
 
+// wide rows, feature-first layout (xyz_col0 == c, c % 4 == 0, 16-byte aligned rows): lanes move float4 columns, two
+// output rows per warp in flight
+__global__ void __launch_bounds__(256)
+group_rows_wide4_kernel(long long rows, int n, int m, int nsample, int c, int pts_stride, int feat_stride,
+                        int feat_offset, int out_stride, const float *__restrict__ pts,
+                        const float *__restrict__ feats, const float *__restrict__ centers,
+                        const int32_t *__restrict__ idx, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long per_cloud = (long long)m * nsample;
+    const long long warp0 = (blockIdx.x * 256LL + threadIdx.x) >> 5, nwarp = ((long long)gridDim.x * 256) >> 5;
+    const int c4 = c >> 2, o4 = out_stride >> 2;   // float4 columns: [0, c4) features, c4 = {xyz - centre, 0}, then zeros
+    for (long long r0 = 2 * warp0; r0 < rows; r0 += 2 * nwarp) {
+        long long bi[2], j[2];
+        int i[2];
+        bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const long long r = r0 + u;
+            ok[u] = r < rows;
+            bi[u] = ok[u] ? r / per_cloud : 0;
+            j[u] = ok[u] ? (r - bi[u] * per_cloud) / nsample : 0;
+            i[u] = ok[u] ? __ldg(idx + r) : 0;
+        }
+        for (int col = lane; col < o4; col += 32) {
+            float4 v[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok[u]) {
+                    if (col < c4) {
+                        v[u] = __ldg(reinterpret_cast<const float4 *>(feats + (bi[u] * n + i[u]) * feat_stride + feat_offset) + col);
+                    } else if (col == c4) {
+                        const float *p = pts + (bi[u] * n + i[u]) * pts_stride, *q = centers + (bi[u] * m + j[u]) * 3;
+                        v[u] = make_float4(__ldg(p) - __ldg(q), __ldg(p + 1) - __ldg(q + 1), __ldg(p + 2) - __ldg(q + 2), 0.f);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (ok[u]) reinterpret_cast<float4 *>(out + (r0 + u) * out_stride)[col] = v[u];
+        }
+    }
+}
+
 // Backward of the feature columns, as a GATHER (no atomics, fixed summation order).
 // One CTA per (cloud, slice of source points); one warp per source point i; the lanes first search
 // the 128-ish centre rows in parallel (each row of a ball query is an ascending run of `cnt` distinct
@@ -265,6 +309,10 @@ extern "C" int sg4d_group_rows(int b, int n, int m, int nsample, int c, int pts_
     if (out_stride == 8 && xyz_col0 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
         group_rows_narrow_kernel<8><<<flat_grid(rows), 256, 0, st>>>(rows, n, m, nsample, c, pts_stride, feat_stride,
                                                                     feat_offset, pts, feats, centers, idx, out);
+    } else if (xyz_col0 == c && c > 0 && !(c & 3) && !(out_stride & 3) && !(feat_stride & 3) && !(feat_offset & 3) &&
+               !((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(feats)) & 15)) {
+        group_rows_wide4_kernel<<<flat_grid(rows * 16), 256, 0, st>>>(rows, n, m, nsample, c, pts_stride, feat_stride,
+                                                                     feat_offset, out_stride, pts, feats, centers, idx, out);
     } else {
         group_rows_wide_kernel<<<flat_grid(rows * 32), 256, 0, st>>>(rows, n, m, nsample, c, pts_stride, feat_stride,
                                                                     feat_offset, out_stride, xyz_col0, pts, feats,

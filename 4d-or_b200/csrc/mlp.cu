@@ -146,7 +146,7 @@ struct RowGemmArgs {
     uint8_t *garg;           // (R/S, N)
     const float *E;          // EMODE 1: (R, N) pre-activation of the layer whose ReLU is differentiated
     const float *es, *et, *ei, *em;   // (N) each
-    int dbg_no_tma, dbg_no_mma, dbg_no_load;
+    int dbg_no_tma, dbg_no_mma, dbg_no_load, dbg_no_epi;
 };
 
 template <int N>
@@ -160,8 +160,10 @@ struct RowSmem {
     static constexpr int kTotal = 1024 + kStages * kStageBytes + kCBytes + kConst + 128;
 };
 
-template <int N, int PMODE, int EMODE>
-__global__ void __launch_bounds__(kMlpThreads, 1) row_gemm_kernel(RowGemmArgs p) {
+// PT = producer threads: 256, or 512 for layers with many k-blocks per tile (K >= 128), which are producer-bound
+template <int N, int PMODE, int EMODE, int PT>
+__global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowGemmArgs p) {
+    constexpr int kProdThreads = PT, kProdWarps = PT / 32, kProdRows = kTileM * 8 / PT, kMlpThreads = PT + 32 + kEpiThreads;
     using SM = RowSmem<N>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 1024-byte aligned (swizzle atoms)
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) row_gemm_kernel(RowGemmArgs p)
                 const long long tile = blockIdx.x + (q / nkb) * gridDim.x;
                 const int kb = (int)(q % nkb);
 #pragma unroll
-                for (int i = 0; i < kProdRows; ++i) op_load<PMODE>(p.op, tile * kTileM + r0 + 32 * i, p.R, kb * kKB + 4 * c, dst[i]);
+                for (int i = 0; i < kProdRows; ++i) op_load<PMODE>(p.op, tile * kTileM + r0 + (PT / 8) * i, p.R, kb * kKB + 4 * c, dst[i]);
             }
         };
 #pragma unroll
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) row_gemm_kernel(RowGemmArgs p)
                     const int col = kb * kKB + 4 * c;
 #pragma unroll
                     for (int i = 0; i < kProdRows; ++i) {
-                        const int r = r0 + 32 * i;
+                        const int r = r0 + (PT / 8) * i;
                         const float4 v = op_apply<PMODE>(p.op, buf[j][i], tile * kTileM + r, p.R, col, s_s, s_t, s_p);
                         float4 hi, lo;
                         split4(v, hi, lo);
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) row_gemm_kernel(RowGemmArgs p)
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 
             const long long row0 = tile * kTileM;
-            const int nvalid = (int)min((long long)kTileM, p.R - row0);
+            const int nvalid = p.dbg_no_epi ? 0 : (int)min((long long)kTileM, p.R - row0);
             constexpr int kVecPerRow = N / 4;
             constexpr int kRowStep = kEpiThreads / kVecPerRow;   // rows between two float4 items of one thread
             if (EMODE == 1) {
@@ -725,21 +727,25 @@ __global__ void partial_sum_kernel(int N, int nparts, const double *__restrict__
     out[N + c] = (float)q;
 }
 
-template <int N, int PM, int EM>
+template <int N, int PM, int EM, int PT>
 static int launch_row(const RowGemmArgs &a0, int grid, cudaStream_t stream) {
     RowGemmArgs a = a0;
     a.dbg_no_mma = getenv("SG4D_DBG_NOMMA") != nullptr, a.dbg_no_load = getenv("SG4D_DBG_NOLOAD") != nullptr;
-    auto kern = row_gemm_kernel<N, PM, EM>;
+    a.dbg_no_epi = getenv("SG4D_DBG_NOEPI") != nullptr;
+    auto kern = row_gemm_kernel<N, PM, EM, PT>;
     const int smem = RowSmem<N>::kTotal;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return status_of(e);
-    kern<<<grid, kMlpThreads, smem, stream>>>(a);
+    kern<<<grid, PT + 32 + kEpiThreads, smem, stream>>>(a);
     return SG4D_LAUNCH_CHECK();
 }
 
 template <int PM, int EM>
 static int launch_row_n(int n, const RowGemmArgs &a, int grid, cudaStream_t stream) {
-    return n == 128 ? launch_row<128, PM, EM>(a, grid, stream) : launch_row<64, PM, EM>(a, grid, stream);
+    static const int force = getenv("SG4D_ROW_PT") ? atoi(getenv("SG4D_ROW_PT")) : 0;
+    const bool wide = force == 512;   // measured: 16 producer warps do not pay for T1 (80-register cap, epilogue-bound)
+    if (wide) return n == 128 ? launch_row<128, PM, EM, 512>(a, grid, stream) : launch_row<64, PM, EM, 512>(a, grid, stream);
+    return n == 128 ? launch_row<128, PM, EM, 256>(a, grid, stream) : launch_row<64, PM, EM, 256>(a, grid, stream);
 }
 
 template <int N, int PM, int QM>

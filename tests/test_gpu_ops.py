@@ -271,6 +271,33 @@ def test_group_rows_forward_backward(cuda, c, feat_stride, feat_off, n, m, ns):
         assert torch.equal(g1, fd.grad)
 
 
+@pytest.mark.parametrize("c,n,m,ns", [(192, 512, 128, 64), (64, 300, 33, 16), (8, 1000, 50, 32)])
+def test_group_rows_feature_first_layout(cuda, c, n, m, ns):
+    """[feats | xyz - centre | 0-pad] rows (float4 kernel) hold the same values as the reference order, permuted;
+    backward sums the feature columns back deterministically"""
+    from sg4d import rows
+    b = 2
+    g = torch.Generator().manual_seed(c + n)
+    xyz = _clouds(c + n + 1, b, n, "gauss")
+    feats = torch.randn(b, n, c, generator=g)
+    fps = ora.furthest_point_sampling(xyz, m)
+    new_xyz = ora.gather_points(xyz.transpose(1, 2).contiguous(), fps).transpose(1, 2).contiguous()
+    idx, cnt = rows.ball_query_rows(new_xyz.to(cuda), xyz.to(cuda), [0.3], [ns])
+    stride = (3 + c + 3) // 4 * 4
+    fd = feats.to(cuda).requires_grad_(True)
+    ref = rows.group_rows(xyz.to(cuda), fd, new_xyz.to(cuda), idx[0], cnt[0], c, 0, stride, xyz_last=False)
+    out = rows.group_rows(xyz.to(cuda), fd, new_xyz.to(cuda), idx[0], cnt[0], c, 0, stride, xyz_last=True)
+    assert torch.equal(out[..., :c], ref[..., 3:3 + c]) and torch.equal(out[..., c:c + 3], ref[..., :3])
+    assert float(out[..., c + 3:].abs().sum()) == 0.0
+    w = torch.randn(b, m, ns, stride, generator=g).to(cuda)
+    (out * w).sum().backward()
+    g1 = fd.grad.clone()
+    fd.grad = None
+    w_ref = torch.cat([w[..., c:c + 3], w[..., :c], w[..., c + 3:]], dim=-1)
+    (ref * w_ref).sum().backward()
+    assert torch.equal(g1, fd.grad)
+
+
 def test_gnn_gather_and_scatter(cuda):
     from sg4d import rows
     g = torch.Generator().manual_seed(9)
