@@ -30,7 +30,7 @@ template <int NSC>
 __global__ void __launch_bounds__(kBqWarps * 32)
 ball_query_kernel(int n, int n_scan, int m, int pts_stride, int ctr_stride, int ctas_per_cloud,
                   const float *__restrict__ centers, const float *__restrict__ pts, BqScale s0,
-                  BqScale s1) {
+                  BqScale s1, int *__restrict__ todo_cnt, int *__restrict__ todo_list, int todo_cap) {
     __shared__ float sx[kBqTile], sy[kBqTile], sz[kBqTile];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cloud = blockIdx.x / ctas_per_cloud;
@@ -94,12 +94,19 @@ ball_query_kernel(int n, int n_scan, int m, int pts_stride, int ctr_stride, int 
             for (int p = cnt[s] + lane; p < sc[s].ns; p += 32) row[s][p] = first[s];
             if (sc[s].cnt && lane == 0) sc[s].cnt[(size_t)cloud * m + j] = cnt[s];
         }
+        // prefix pass (n_scan < n): centres still short of nsample hits are queued for the spatial-index pass
+        if (todo_cnt && lane == 0) {
+            bool shortfall = false;
+#pragma unroll
+            for (int s = 0; s < NSC; ++s) shortfall = shortfall || (cnt[s] < sc[s].ns);
+            if (shortfall) todo_list[(size_t)cloud * todo_cap + atomicAdd(todo_cnt + cloud, 1)] = j;
+        }
     }
 }
 
 int bq_launch(int b, int n, int n_scan, int m, int pts_stride, int ctr_stride, int nsc, const float *radius,
                      const int *nsample, const float *centers, const float *pts, int32_t *const *idx,
-                     int32_t *const *cnt, cudaStream_t stream) {
+                     int32_t *const *cnt, cudaStream_t stream, int *todo_cnt, int *todo_list, int todo_cap) {
     BqScale sc[2] = {{0.f, 0, nullptr, nullptr}, {0.f, 0, nullptr, nullptr}};
     for (int s = 0; s < nsc; ++s) {
         if (nsample[s] <= 0 || !idx[s]) return SG4D_EINVAL;
@@ -114,10 +121,10 @@ int bq_launch(int b, int n, int n_scan, int m, int pts_stride, int ctr_stride, i
     if (grid > 0x7fffffffLL) return SG4D_EINVAL;
     if (nsc == 1)
         ball_query_kernel<1><<<(unsigned)grid, kBqWarps * 32, 0, stream>>>(n, n_scan, m, pts_stride, ctr_stride, cpc,
-                                                                          centers, pts, sc[0], sc[1]);
+                                                                          centers, pts, sc[0], sc[1], todo_cnt, todo_list, todo_cap);
     else
         ball_query_kernel<2><<<(unsigned)grid, kBqWarps * 32, 0, stream>>>(n, n_scan, m, pts_stride, ctr_stride, cpc,
-                                                                          centers, pts, sc[0], sc[1]);
+                                                                          centers, pts, sc[0], sc[1], todo_cnt, todo_list, todo_cap);
     return SG4D_LAUNCH_CHECK();
 }
 

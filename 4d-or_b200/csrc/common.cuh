@@ -84,7 +84,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
 // ball_query.cu: brute-force scan of the first n_scan points of every cloud (n_scan == n: the complete query)
 int bq_launch(int b, int n, int n_scan, int m, int pts_stride, int ctr_stride, int nsc, const float *radius,
               const int *nsample, const float *centers, const float *pts, int32_t *const *idx, int32_t *const *cnt,
-              cudaStream_t stream);
+              cudaStream_t stream, int *todo_cnt = nullptr, int *todo_list = nullptr, int todo_cap = 0);
 
 inline int status_of(cudaError_t e) { return e == cudaSuccess ? SG4D_OK : static_cast<int>(e); }
 

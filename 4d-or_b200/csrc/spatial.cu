@@ -41,6 +41,7 @@ constexpr int kBuildThreads = 1024;
 constexpr int kFpsThreads = 256;
 constexpr int kFpsWarps = kFpsThreads / 32;
 constexpr int kMaxBuckets = 6144;         // 32 B of shared memory per bucket in the FPS kernel
+constexpr int kTodoCap = 1024;            // centres per cloud the ball query's todo list can hold (larger m: no list)
 
 // ---- layout of one cloud's index inside the workspace (all arrays 128-byte aligned) ----
 constexpr int kBoxSlices = 16;            // CTAs per cloud of the bounding-box pre-pass
@@ -478,26 +479,27 @@ __device__ __forceinline__ void warp_sort128(uint32_t *buf, int lane) {
 template <int NSC>
 __global__ void __launch_bounds__(kBqiWarps * 32)
 ball_query_indexed_kernel(int n, int m, int ctr_stride, int ctas_per_cloud, const float *__restrict__ centers,
-                          const float *__restrict__ ws, long long ws_words, int only_unfinished, BqiScale s0,
-                          BqiScale s1) {
+                          const float *__restrict__ ws, long long ws_words, const int *__restrict__ todo_cnt,
+                          const int *__restrict__ todo_list, int todo_cap, BqiScale s0, BqiScale s1) {
     extern __shared__ float s_box[];                        // 6 x nbp bucket boxes of this cloud
     __shared__ uint32_t s_buf[kBqiWarps][2][kBqiCap];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const int cloud = blockIdx.x / ctas_per_cloud;
-    const int j = (blockIdx.x % ctas_per_cloud) * kBqiWarps + warp;
+    const int slot = (blockIdx.x % ctas_per_cloud) * kBqiWarps + warp;
     const IndexLayout lay = index_layout(n);
     const int nb = lay.nb, nbp = (nb + 31) / 32 * 32;
     ws += (size_t)cloud * ws_words;
     const float4 *P4 = reinterpret_cast<const float4 *>(ws + lay.p4);
     BqiScale sc[2] = {s0, s1};
 
-    bool todo = j < m;
-    if (todo && only_unfinished) {   // the prefix scan (ball_query.cu) already completed this centre?
-        bool fin = true;
-#pragma unroll
-        for (int s = 0; s < NSC; ++s) fin = fin && (__ldg(sc[s].cnt + (size_t)cloud * m + j) >= sc[s].ns);
-        todo = !fin;
+    // with a todo list (written by the prefix pass) the CTAs of a cloud are filled densely with the centres that
+    // still need an answer; the remaining CTAs exit before touching the index
+    int j = slot;
+    bool todo = slot < m;
+    if (todo_cnt) {
+        todo = slot < __ldg(todo_cnt + cloud);
+        j = todo ? __ldg(todo_list + (size_t)cloud * todo_cap + slot) : 0;
     }
     if (!__syncthreads_or(todo)) return;
     for (int i = tid; i < 6 * nbp; i += kBqiWarps * 32) s_box[i] = __ldg(ws + lay.lox + i);
@@ -527,6 +529,26 @@ ball_query_indexed_kernel(int n, int m, int ctr_stride, int ctas_per_cloud, cons
         __syncwarp();
     };
 
+    auto scan_bucket = [&](const float4 &a0, const float4 &a1) {
+        const float d0 = sqdist3(qx - a0.x, qy - a0.y, qz - a0.z);
+        const float d1 = sqdist3(qx - a1.x, qy - a1.y, qz - a1.z);
+        const uint32_t k0 = (uint32_t)__float_as_int(a0.w), k1 = (uint32_t)__float_as_int(a1.w);
+#pragma unroll
+        for (int s = 0; s < NSC; ++s) {
+            const bool h0 = d0 < sc[s].r2, h1 = d1 < sc[s].r2;   // ordered compares: NaN never hits
+            const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+            if ((m0 | m1) == 0u) continue;
+            total[s] += __popc(m0) + __popc(m1);
+            const bool w0 = h0 && k0 < thr[s], w1 = h1 && k1 < thr[s];
+            const unsigned e0 = __ballot_sync(0xffffffffu, w0), e1 = __ballot_sync(0xffffffffu, w1);
+            if (w0) buf[s][held[s] + __popc(e0 & lt)] = k0;
+            if (w1) buf[s][held[s] + __popc(e0) + __popc(e1 & lt)] = k1;
+            held[s] += __popc(e0) + __popc(e1);
+            __syncwarp();
+            if (held[s] > kBqiCap - kBucket) compact(s);
+        }
+    };
+
     for (int b0 = 0; b0 < nbp; b0 += 32) {
         const int b = b0 + lane;
         bool near = false;
@@ -536,28 +558,18 @@ ball_query_indexed_kernel(int n, int m, int ctr_stride, int ctas_per_cloud, cons
             near = bound < rmax;
         }
         unsigned mask = __ballot_sync(0xffffffffu, near);
-        while (mask) {
-            const int bb = b0 + __ffs(mask) - 1;
+        while (mask) {   // two candidate buckets per trip: the second one's loads overlap the first one's selection
+            const int b1 = b0 + __ffs(mask) - 1;
             mask &= mask - 1;
-            const long long p = (long long)bb * kBucket + lane;
-            const float4 a0 = __ldg(P4 + p), a1 = __ldg(P4 + p + 32);
-            const float d0 = sqdist3(qx - a0.x, qy - a0.y, qz - a0.z);
-            const float d1 = sqdist3(qx - a1.x, qy - a1.y, qz - a1.z);
-            const uint32_t k0 = (uint32_t)__float_as_int(a0.w), k1 = (uint32_t)__float_as_int(a1.w);
-#pragma unroll
-            for (int s = 0; s < NSC; ++s) {
-                const bool h0 = d0 < sc[s].r2, h1 = d1 < sc[s].r2;   // ordered compares: NaN never hits
-                const unsigned a0 = __ballot_sync(0xffffffffu, h0), a1 = __ballot_sync(0xffffffffu, h1);
-                if ((a0 | a1) == 0u) continue;
-                total[s] += __popc(a0) + __popc(a1);
-                const bool w0 = h0 && k0 < thr[s], w1 = h1 && k1 < thr[s];
-                const unsigned e0 = __ballot_sync(0xffffffffu, w0), e1 = __ballot_sync(0xffffffffu, w1);
-                if (w0) buf[s][held[s] + __popc(e0 & lt)] = k0;
-                if (w1) buf[s][held[s] + __popc(e0) + __popc(e1 & lt)] = k1;
-                held[s] += __popc(e0) + __popc(e1);
-                __syncwarp();
-                if (held[s] > kBqiCap - kBucket) compact(s);
-            }
+            const bool two = mask != 0u;
+            const int b2 = two ? b0 + __ffs(mask) - 1 : b1;
+            mask &= mask - 1;
+            const long long p1 = (long long)b1 * kBucket + lane, p2 = (long long)b2 * kBucket + lane;
+            const float4 a0 = __ldg(P4 + p1), a1 = __ldg(P4 + p1 + 32);
+            float4 c0 = a0, c1 = a1;
+            if (two) c0 = __ldg(P4 + p2), c1 = __ldg(P4 + p2 + 32);
+            scan_bucket(a0, a1);
+            if (two) scan_bucket(c0, c1);
         }
     }
 #pragma unroll
@@ -583,10 +595,11 @@ static int floor_log2_i(int v) {
 
 using namespace sg4d;
 
+// workspace = b per-cloud indices, then the ball query's todo lists: b counters followed by b x kTodoCap centre ids
 extern "C" long long sg4d_spatial_index_bytes(int b, int n) {
     if (b < 0 || n <= 0) return 0;
     const IndexLayout lay = index_layout(n);
-    return (long long)b * ((lay.words + 31) / 32 * 32) * 4;
+    return (long long)b * ((lay.words + 31) / 32 * 32) * 4 + ((long long)b * (1 + kTodoCap) + 32) * 4;
 }
 
 static long long ws_words_of(int n) { return (index_layout(n).words + 31) / 32 * 32; }
@@ -629,24 +642,20 @@ extern "C" int sg4d_fps_indexed(int b, int n, int m, int row_stride, const float
     return SG4D_LAUNCH_CHECK();
 }
 
-static int ball_query_indexed(int b, int n, int m, int center_stride, int nscales, const float *radius,
-                              const int *nsample, const float *centers, const void *index, int32_t *const *idx,
-                              int32_t *const *cnt, int only_unfinished, sg4d_stream_t stream) {
-    if (b < 0 || n <= 0 || m < 0 || center_stride < 3 || nscales < 1 || nscales > SG4D_MAX_SCALES || !radius ||
-        !nsample || !centers || !index || !idx || !sg4d_spatial_index_supported(n) || (only_unfinished && !cnt))
-        return SG4D_EINVAL;
-    if (b == 0 || m == 0) return SG4D_OK;
+// one pass (<= 2 scales) answered from the index; todo_cnt != nullptr: only the centres queued by the prefix pass
+static int ball_query_indexed_pass(int b, int n, int m, int center_stride, int k, const float *radius,
+                                   const int *nsample, const float *centers, const void *index, int32_t *const *idx,
+                                   int32_t *const *cnt, const int *todo_cnt, const int *todo_list, sg4d_stream_t stream) {
     const int nbp = (index_layout(n).nb + 31) / 32 * 32;
     const size_t smem = (size_t)nbp * 6 * 4;
     const int cpc = (m + kBqiWarps - 1) / kBqiWarps;
     const long long grid = (long long)b * cpc;
     if (grid > 0x7fffffffLL) return SG4D_EINVAL;
-    for (int s = 0; s < nscales; s += 2) {
-        const int k = nscales - s >= 2 ? 2 : 1;
+    {
+        const int s = 0;
         BqiScale sc[2] = {{0.f, 0, nullptr, nullptr}, {0.f, 0, nullptr, nullptr}};
         for (int u = 0; u < k; ++u) {
             if (nsample[s + u] <= 0 || nsample[s + u] > kBqiMaxNs || !idx[s + u]) return SG4D_EINVAL;
-            if (only_unfinished && !cnt[s + u]) return SG4D_EINVAL;
             const float r = radius[s + u];
             sc[u].r2 = r * r;
             sc[u].ns = nsample[s + u];
@@ -658,12 +667,12 @@ static int ball_query_indexed(int b, int n, int m, int center_stride, int nscale
             e = cudaFuncSetAttribute(ball_query_indexed_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return status_of(e);
             ball_query_indexed_kernel<1><<<(unsigned)grid, kBqiWarps * 32, smem, (cudaStream_t)stream>>>(
-                n, m, center_stride, cpc, centers, (const float *)index, ws_words_of(n), only_unfinished, sc[0], sc[1]);
+                n, m, center_stride, cpc, centers, (const float *)index, ws_words_of(n), todo_cnt, todo_list, kTodoCap, sc[0], sc[1]);
         } else {
             e = cudaFuncSetAttribute(ball_query_indexed_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return status_of(e);
             ball_query_indexed_kernel<2><<<(unsigned)grid, kBqiWarps * 32, smem, (cudaStream_t)stream>>>(
-                n, m, center_stride, cpc, centers, (const float *)index, ws_words_of(n), only_unfinished, sc[0], sc[1]);
+                n, m, center_stride, cpc, centers, (const float *)index, ws_words_of(n), todo_cnt, todo_list, kTodoCap, sc[0], sc[1]);
         }
         const int st = SG4D_LAUNCH_CHECK();
         if (st != SG4D_OK) return st;
@@ -676,22 +685,37 @@ extern "C" int sg4d_ball_query_rows_indexed(int b, int n, int m, int row_stride,
                                             const float *pts, const void *index, int prefix, int32_t *const *idx,
                                             int32_t *const *cnt, sg4d_stream_t stream) {
     if (b < 0 || n <= 0 || m < 0 || row_stride < 3 || center_stride < 3 || nscales < 1 || nscales > SG4D_MAX_SCALES ||
-        !radius || !nsample || !centers || !pts || !index || !idx || prefix < 0 || (prefix > 0 && !cnt))
+        !radius || !nsample || !centers || !pts || !index || !idx || prefix < 0 || (prefix > 0 && !cnt) ||
+        !sg4d_spatial_index_supported(n))
         return SG4D_EINVAL;
     if (b == 0 || m == 0) return SG4D_OK;
     if (prefix > n) prefix = n;
-    if (prefix > 0) {
-        // pass 1: brute force over the first `prefix` points with early exit -- centres in dense regions find their
-        // nsample lowest-index neighbours within a few hundred points and never need the index
-        for (int s = 0; s < nscales; s += 2) {
-            const int k = nscales - s >= 2 ? 2 : 1;
-            const int st = bq_launch(b, n, prefix, m, row_stride, center_stride, k, radius + s, nsample + s, centers, pts,
-                                     idx + s, cnt + s, (cudaStream_t)stream);
+    if (m > kTodoCap) prefix = 0;   // no room for the todo list: answer every centre from the index
+    int *todo_cnt = reinterpret_cast<int *>(const_cast<char *>(static_cast<const char *>(index)) + (size_t)b * ws_words_of(n) * 4);
+    int *todo_list = todo_cnt + (b + 31) / 32 * 32;
+    for (int s = 0; s < nscales; s += 2) {   // two radii per pass over the cloud
+        const int k = nscales - s >= 2 ? 2 : 1;
+        if (prefix > 0) {
+            for (int u = 0; u < k; ++u)
+                if (!cnt[s + u]) return SG4D_EINVAL;
+            // pass 1: brute force over the first `prefix` points with early exit -- centres in dense regions find
+            // their nsample lowest-index neighbours within a few hundred points and never need the index; the others
+            // are queued per cloud
+            cudaError_t e = cudaMemsetAsync(todo_cnt, 0, (size_t)b * sizeof(int), (cudaStream_t)stream);
+            if (e != cudaSuccess) return status_of(e);
+            int st = bq_launch(b, n, prefix, m, row_stride, center_stride, k, radius + s, nsample + s, centers, pts, idx + s,
+                               cnt + s, (cudaStream_t)stream, todo_cnt, todo_list, kTodoCap);
+            if (st != SG4D_OK) return st;
+            if (prefix == n) continue;
+            // pass 2: the queued centres are answered exactly from the spatial index
+            st = ball_query_indexed_pass(b, n, m, center_stride, k, radius + s, nsample + s, centers, index, idx + s, cnt + s,
+                                         todo_cnt, todo_list, stream);
+            if (st != SG4D_OK) return st;
+        } else {
+            const int st = ball_query_indexed_pass(b, n, m, center_stride, k, radius + s, nsample + s, centers, index, idx + s,
+                                                   cnt ? cnt + s : nullptr, nullptr, nullptr, stream);
             if (st != SG4D_OK) return st;
         }
-        if (prefix == n) return SG4D_OK;
     }
-    // pass 2: every centre that is still short of nsample hits is answered exactly from the spatial index
-    return ball_query_indexed(b, n, m, center_stride, nscales, radius, nsample, centers, index, idx, cnt, prefix > 0,
-                              stream);
+    return SG4D_OK;
 }

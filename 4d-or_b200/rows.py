@@ -10,7 +10,7 @@ from . import _lib
 
 _ONCHIP_MAX_POINTS = 16 * 1024 * 12
 INDEX_MIN_POINTS = 12288    # clouds larger than this go through the spatial index (csrc/spatial.cu)
-BALL_QUERY_PREFIX = 4096    # points scanned by brute force before the index answers the remaining centres
+BALL_QUERY_PREFIX = 2048    # points scanned by brute force before the index answers the remaining centres
 
 
 def _rows_ok(t, name):

@@ -341,6 +341,16 @@ def main_sg4d(args):
         elif nm == "sg4d_group_rows_grad":
             b_, n_, m_, ns_, c_ = a[:5]
             bts = b_ * (4 * c_ * m_ * ns_ + 4 * m_ * ns_ + 4 * c_ * n_)
+        elif nm == "sg4d_linear_fwd":            # (rows, k, lda, n, group): read the operand rows, write the pre-activations
+            bts = a[0] * 4 * (a[1] + a[3])
+        elif nm == "sg4d_pool_bwd_da":           # (rows, C2, C1, group): read y2, y1; write dz1
+            bts = a[0] * 4 * (a[1] + 2 * a[2])
+        elif nm == "sg4d_pool_bwd_dw":           # (rows, C2, C1, group): read y2, y1
+            bts = a[0] * 4 * (a[1] + a[2])
+        elif nm == "sg4d_inner_bwd_dx":          # (rows, C1, n): read y1, dz1; write n columns of dX
+            bts = a[0] * 4 * (2 * a[1] + a[2])
+        elif nm == "sg4d_inner_bwd_dw":          # (rows, C1, k, ldx): read y1, dz1, x
+            bts = a[0] * 4 * (2 * a[1] + a[2])
         elif nm in ("sg4d_ball_query_rows", "sg4d_ball_query_rows_indexed"):
             b_, n_, m_ = a[:3]
             bts = b_ * (12 * n_ + 12 * m_)                                # + 4*m*sum(ns) (small)
