@@ -26,6 +26,9 @@ SIGNATURES = {
     "sg4d_ball_query": [_i, _i, _i, _f, _i, _p, _p, _p, _p],
     "sg4d_group_points": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
     "sg4d_group_points_grad": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
+    "sg4d_three_nn": [_i, _i, _i, _p, _p, _p, _p, _p],
+    "sg4d_three_interpolate": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "sg4d_three_interpolate_grad": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
     "sg4d_fps_rows": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
     "sg4d_ball_query_rows": [_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "sg4d_group_rows": [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],

@@ -5,7 +5,8 @@ allocation and error type as the reference's pybind module ``pointnet2_ops._ext`
 
 Differences, all deliberate: outputs that the kernels fully overwrite are allocated with ``empty``
 instead of ``zeros``; the FPS scratch ``temp`` is only materialised for clouds too large to stay on
-chip; CPU tensors raise ``RuntimeError("CPU not supported")`` exactly like the reference.
+chip; CPU tensors raise ``RuntimeError("CPU not supported")`` exactly like the reference.  All nine functions
+are implemented (the three feature-propagation ops live in ``csrc/interpolate.cu``).
 """
 import torch
 
@@ -99,15 +100,41 @@ def group_points_grad(grad_out, idx, n):
     return out
 
 
-def _out_of_scope(name):
-    def fn(*args, **kwargs):
-        raise NotImplementedError(
-            f"{name}: the feature-propagation ops are outside the scene-graph hot path "
-            "(SURVEY.md section 8, row f4); PointNet2ClassificationMSG never calls them")
-    fn.__name__ = name
-    return fn
+def three_nn(unknowns, knows):
+    """(B,n,3), (B,m,3) -> [dist2 (B,n,3) fp32, idx (B,n,3) int32].  interpolate.cpp:14-40."""
+    _check(unknowns, torch.float32, "unknowns")
+    _check(knows, torch.float32, "knows")
+    _lib.require_cuda(unknowns, knows)
+    b, n, _ = unknowns.shape
+    m = knows.shape[1]
+    dist2 = torch.empty(b, n, 3, dtype=torch.float32, device=unknowns.device)
+    idx = torch.empty(b, n, 3, dtype=torch.int32, device=unknowns.device)
+    _lib.call("sg4d_three_nn", unknowns, b, n, m, unknowns.data_ptr(), knows.data_ptr(), dist2.data_ptr(), idx.data_ptr())
+    return [dist2, idx]
 
 
-three_nn = _out_of_scope("three_nn")
-three_interpolate = _out_of_scope("three_interpolate")
-three_interpolate_grad = _out_of_scope("three_interpolate_grad")
+def three_interpolate(points, idx, weight):
+    """(B,c,m), (B,n,3) int32, (B,n,3) -> (B,c,n).  interpolate.cpp:42-70."""
+    _check(points, torch.float32, "points")
+    _check(idx, torch.int32, "idx")
+    _check(weight, torch.float32, "weight")
+    _lib.require_cuda(points, idx, weight)
+    b, c, m = points.shape
+    n = idx.shape[1]
+    out = torch.empty(b, c, n, dtype=torch.float32, device=points.device)
+    _lib.call("sg4d_three_interpolate", points, b, c, m, n, points.data_ptr(), idx.data_ptr(), weight.data_ptr(),
+              out.data_ptr())
+    return out
+
+
+def three_interpolate_grad(grad_out, idx, weight, m):
+    """(B,c,n), (B,n,3), (B,n,3) -> (B,c,m).  interpolate.cpp:71-99."""
+    _check(grad_out, torch.float32, "grad_out")
+    _check(idx, torch.int32, "idx")
+    _check(weight, torch.float32, "weight")
+    _lib.require_cuda(grad_out, idx, weight)
+    b, c, n = grad_out.shape
+    out = torch.zeros(b, c, m, dtype=torch.float32, device=grad_out.device)
+    _lib.call("sg4d_three_interpolate_grad", grad_out, b, c, n, m, grad_out.data_ptr(), idx.data_ptr(),
+              weight.data_ptr(), out.data_ptr())
+    return out

@@ -153,9 +153,9 @@ class PointnetSAModule(PointnetSAModuleMSG):
 
 
 class PointnetFPModule(nn.Module):
-    """Feature propagation (OPS/pointnet2_modules.py:149-209).  Constructible for API / state_dict
-    compatibility; its forward needs three_nn / three_interpolate, which are outside the scene-graph
-    hot path."""
+    """Feature propagation (OPS/pointnet2_modules.py:149-209) on sg4d's three_nn / three_interpolate kernels
+    (csrc/interpolate.cu).  Not used by the scene-graph encoder; provided so that the package is a complete
+    drop-in for ``pointnet2_ops``."""
 
     def __init__(self, mlp, bn=True):
         super().__init__()

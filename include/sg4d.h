@@ -85,6 +85,23 @@ int sg4d_group_points(int b, int c, int n, int npoints, int nsample, const float
 int sg4d_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
                            const int32_t *idx, float *grad_points, sg4d_stream_t stream);
 
+/* replaces three_nn_kernel_wrapper (interpolate.cpp:4-5, interpolate_gpu.cu:9-70).
+ * unknown (b,n,3), known (b,m,3) fp32 -> dist2 (b,n,3) fp32 = SQUARED distances to the three nearest known points
+ * (ascending; ties keep the lower index), idx (b,n,3) int32.  With m < 3 the missing slots hold index 0 and +inf
+ * (the reference stores (float)1e40). */
+int sg4d_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int32_t *idx,
+                  sg4d_stream_t stream);
+
+/* replaces three_interpolate_kernel_wrapper (interpolate.cpp:6-8, interpolate_gpu.cu:72-114).
+ * points (b,c,m), idx (b,n,3), weight (b,n,3) -> out (b,c,n) */
+int sg4d_three_interpolate(int b, int c, int m, int n, const float *points, const int32_t *idx, const float *weight,
+                           float *out, sg4d_stream_t stream);
+
+/* replaces three_interpolate_grad_kernel_wrapper (interpolate.cpp:9-12, interpolate_gpu.cu:116-154).
+ * grad_out (b,c,n), idx, weight (b,n,3) -> grad_points (b,c,m), ZERO on entry (interpolate.cpp:85-87). */
+int sg4d_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int32_t *idx,
+                                const float *weight, float *grad_points, sg4d_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Section 2 -- fused / point-major entry points used by the host-side model
  *

@@ -1,7 +1,7 @@
 """oracle/pn2_ext_cpu.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
 ctypes front-end to ``oracle/_build/libpn2_oracle.so`` (the plain-C restatement of the reference
-CUDA kernels, ``oracle/pn2_oracle.c``) exposing the same six function names, argument order and
+CUDA kernels, ``oracle/pn2_oracle.c``) exposing the same nine function names, argument order and
 allocation rules as the reference's pybind module ``pointnet2_ops._ext``
 (``_ext-src/src/bindings.cpp:6-19``), but on CPU tensors.  Because the names match it can be
 registered as ``sys.modules['pointnet2_ops._ext']`` underneath the reference's *unmodified*
@@ -45,9 +45,13 @@ def lib():
         L.oracle_ball_query.argtypes = [i, i, i, f, i, p, p, p]
         L.oracle_group_points.argtypes = [i, i, i, i, i, p, p, p]
         L.oracle_group_points_grad.argtypes = [i, i, i, i, i, p, p, p]
+        L.oracle_three_nn.argtypes = [i, i, i, p, p, p, p]
+        L.oracle_three_interpolate.argtypes = [i, i, i, i, p, p, p, p]
+        L.oracle_three_interpolate_grad.argtypes = [i, i, i, i, p, p, p, p]
         for fn in ("oracle_furthest_point_sampling", "oracle_gather_points",
                    "oracle_gather_points_grad", "oracle_ball_query", "oracle_group_points",
-                   "oracle_group_points_grad"):
+                   "oracle_group_points_grad", "oracle_three_nn", "oracle_three_interpolate",
+                   "oracle_three_interpolate_grad"):
             getattr(L, fn).restype = None
         _lib = L
     return _lib
@@ -128,8 +132,34 @@ def group_points_grad(grad_out, idx, n):
     return out
 
 
-def three_nn(*a, **k):  # out of scope
-    raise NotImplementedError("three_nn is outside the hot path")
+def three_nn(unknowns, knows):
+    _chk(unknowns, torch.float32, "unknowns")
+    _chk(knows, torch.float32, "knows")
+    b, n, _ = unknowns.shape
+    m = knows.shape[1]
+    dist2 = torch.zeros(b, n, 3, dtype=torch.float32)
+    idx = torch.zeros(b, n, 3, dtype=torch.int32)
+    lib().oracle_three_nn(b, n, m, unknowns.data_ptr(), knows.data_ptr(), dist2.data_ptr(), idx.data_ptr())
+    return [dist2, idx]
 
 
-three_interpolate = three_interpolate_grad = three_nn
+def three_interpolate(points, idx, weight):
+    _chk(points, torch.float32, "points")
+    _chk(idx, torch.int32, "idx")
+    _chk(weight, torch.float32, "weight")
+    b, c, m = points.shape
+    n = idx.shape[1]
+    out = torch.zeros(b, c, n, dtype=torch.float32)
+    lib().oracle_three_interpolate(b, c, m, n, points.data_ptr(), idx.data_ptr(), weight.data_ptr(), out.data_ptr())
+    return out
+
+
+def three_interpolate_grad(grad_out, idx, weight, m):
+    _chk(grad_out, torch.float32, "grad_out")
+    _chk(idx, torch.int32, "idx")
+    _chk(weight, torch.float32, "weight")
+    b, c, n = grad_out.shape
+    out = torch.zeros(b, c, m, dtype=torch.float32)
+    lib().oracle_three_interpolate_grad(b, c, n, m, grad_out.data_ptr(), idx.data_ptr(), weight.data_ptr(),
+                                        out.data_ptr())
+    return out

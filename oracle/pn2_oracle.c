@@ -187,3 +187,70 @@ void oracle_group_points_grad(int b, int c, int n, int npoints, int nsample,
                         g[((size_t)l * npoints + j) * nsample + k];
     }
 }
+
+/* src/interpolate_gpu.cu:9-59 -- three nearest known points of every unknown point.  Literal restatement: k ascending,
+ * strict '<' against doubles initialised to 1e40 (so +inf and NaN distances never enter), distances in the SASS order
+ * of the reference build (t = dy*dy; t = fma(dx,dx,t); d = fma(dz,dz,t)); outputs stored as float (1e40 -> +inf). */
+void oracle_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int32_t *idx) {
+#pragma omp parallel for schedule(static)
+    for (int bi = 0; bi < b; ++bi) {
+        const float *u = unknown + (size_t)bi * n * 3, *kn = known + (size_t)bi * m * 3;
+        for (int j = 0; j < n; ++j) {
+            const float ux = u[3 * j], uy = u[3 * j + 1], uz = u[3 * j + 2];
+            double best1 = 1e40, best2 = 1e40, best3 = 1e40;
+            int besti1 = 0, besti2 = 0, besti3 = 0;
+            for (int k = 0; k < m; ++k) {
+                const float d = sqdist3(ux - kn[3 * k], uy - kn[3 * k + 1], uz - kn[3 * k + 2]);
+                if (d < best1) {
+                    best3 = best2, besti3 = besti2, best2 = best1, besti2 = besti1, best1 = d, besti1 = k;
+                } else if (d < best2) {
+                    best3 = best2, besti3 = besti2, best2 = d, besti2 = k;
+                } else if (d < best3) {
+                    best3 = d, besti3 = k;
+                }
+            }
+            float *o = dist2 + ((size_t)bi * n + j) * 3;
+            int32_t *oi = idx + ((size_t)bi * n + j) * 3;
+            o[0] = (float)best1, o[1] = (float)best2, o[2] = (float)best3;
+            oi[0] = besti1, oi[1] = besti2, oi[2] = besti3;
+        }
+    }
+}
+
+/* src/interpolate_gpu.cu:72-101 -- out[b,l,j] = p[i1]*w1 + p[i2]*w2 + p[i3]*w3, contracted by nvcc as
+ * t = p[i2]*w2; t = fma(p[i1],w1,t); out = fma(p[i3],w3,t)  (read from the SASS of the reference build) */
+void oracle_three_interpolate(int b, int c, int m, int n, const float *points, const int32_t *idx,
+                              const float *weight, float *out) {
+#pragma omp parallel for schedule(static)
+    for (int bi = 0; bi < b; ++bi)
+        for (int l = 0; l < c; ++l) {
+            const float *p = points + ((size_t)bi * c + l) * m;
+            for (int j = 0; j < n; ++j) {
+                const int32_t *ix = idx + ((size_t)bi * n + j) * 3;
+                const float *w = weight + ((size_t)bi * n + j) * 3;
+                float t = p[ix[1]] * w[1];
+                t = fmaf(p[ix[0]], w[0], t);
+                out[((size_t)bi * c + l) * n + j] = fmaf(p[ix[2]], w[2], t);
+            }
+        }
+}
+
+/* src/interpolate_gpu.cu:116-143 -- grad_points[b,l,i_t] += grad_out[b,l,j] * w_t (atomicAdd in the reference; here
+ * the fixed order j ascending, t = 1, 2, 3) */
+void oracle_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int32_t *idx,
+                                   const float *weight, float *grad_points) {
+    memset(grad_points, 0, sizeof(float) * (size_t)b * c * m);
+#pragma omp parallel for schedule(static)
+    for (int bi = 0; bi < b; ++bi)
+        for (int l = 0; l < c; ++l) {
+            float *gp = grad_points + ((size_t)bi * c + l) * m;
+            for (int j = 0; j < n; ++j) {
+                const int32_t *ix = idx + ((size_t)bi * n + j) * 3;
+                const float *w = weight + ((size_t)bi * n + j) * 3;
+                const float g = grad_out[((size_t)bi * c + l) * n + j];
+                gp[ix[0]] += g * w[0];
+                gp[ix[1]] += g * w[1];
+                gp[ix[2]] += g * w[2];
+            }
+        }
+}

@@ -298,6 +298,56 @@ def test_group_rows_feature_first_layout(cuda, c, n, m, ns):
     assert torch.equal(g1, fd.grad)
 
 
+@pytest.mark.parametrize("b,n,m,c", [(3, 700, 150, 5), (2, 2048, 512, 64), (2, 64, 2, 3), (2, 300, 1, 4), (1, 9000, 2500, 8)])
+def test_three_nn_and_interpolate_match_oracle(cuda, b, n, m, c):
+    """feature-propagation ops through the C ABI: index / distance / interpolation
+    outputs bit-exact vs the oracle, the atomics-based gradient within 2e-5"""
+    e = _ext()
+    g = torch.Generator().manual_seed(n + m)
+    unknown, known = torch.rand(b, n, 3, generator=g), torch.rand(b, m, 3, generator=g)
+    if m > 8:
+        known[0, 7] = known[0, 3]
+        known[0, 1] = float("nan")                              # never selected
+    od, oi = ora.three_nn(unknown, known)
+    sd, si = e.three_nn(unknown.to(cuda), known.to(cuda))
+    np.testing.assert_array_equal(si.cpu().numpy(), oi.numpy())
+    np.testing.assert_array_equal(sd.cpu().numpy(), od.numpy())
+    feats = torch.randn(b, c, m, generator=g)
+    w = torch.rand(b, n, 3, generator=g)
+    np.testing.assert_array_equal(e.three_interpolate(feats.to(cuda), si, w.to(cuda)).cpu().numpy(),
+                                  ora.three_interpolate(feats, oi, w).numpy())
+    go = torch.randn(b, c, n, generator=g)
+    torch.testing.assert_close(e.three_interpolate_grad(go.to(cuda), si, w.to(cuda), m).cpu(),
+                               ora.three_interpolate_grad(go, oi, w, m), rtol=1e-5, atol=2e-5)
+
+
+def test_fp_module_forward_backward(cuda):
+    """PointnetFPModule (OPS/pointnet2_modules.py:149-209) on the sg4d ops vs the same module arithmetic in torch"""
+    from sg4d.pointnet2_ops.pointnet2_modules import PointnetFPModule
+    torch.manual_seed(3)
+    fp = PointnetFPModule(mlp=[6 + 4, 16, 8]).to(cuda).train()
+    g = torch.Generator().manual_seed(4)
+    unknown, known = torch.rand(2, 200, 3, generator=g).to(cuda), torch.rand(2, 40, 3, generator=g).to(cuda)
+    uf = torch.randn(2, 4, 200, generator=g).to(cuda)
+    kf = torch.randn(2, 6, 40, generator=g).to(cuda).requires_grad_(True)
+    out = fp(unknown, known, uf, kf)
+    out.sum().backward()
+    g1 = kf.grad.clone()
+    # the same maths with dense torch ops
+    kf2 = kf.detach().clone().requires_grad_(True)
+    d = ((unknown[:, :, None, :] - known[:, None, :, :]) ** 2).sum(-1).sqrt()
+    dist, idx = torch.sort(d, dim=2, stable=True)
+    dist, idx = dist[:, :, :3], idx[:, :, :3]
+    rec = 1.0 / (dist + 1e-8)
+    wgt = rec / rec.sum(2, keepdim=True)
+    gathered = torch.gather(kf2[:, :, None, :].expand(-1, -1, 200, -1), 3, idx[:, None].expand(-1, 6, -1, -1))
+    interp = (gathered * wgt[:, None]).sum(-1)
+    out2 = fp.mlp(torch.cat([interp, uf], dim=1).unsqueeze(-1)).squeeze(-1)
+    out2.sum().backward()
+    torch.testing.assert_close(out, out2, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(g1, kf2.grad, rtol=1e-3, atol=1e-4)
+
+
 def test_gnn_gather_and_scatter(cuda):
     from sg4d import rows
     g = torch.Generator().manual_seed(9)

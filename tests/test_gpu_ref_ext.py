@@ -70,3 +70,29 @@ def test_reference_gather_group_kernels_equal_oracle_and_sg4d(cuda, ref):
                                rtol=0, atol=1e-5)
     torch.testing.assert_close(_ext.group_points_grad(d(go), d(i2), n).cpu(), ref.group_points_grad(d(go), d(i2), n).cpu(),
                                rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("b,n,m,c", [(3, 700, 150, 5), (2, 2048, 512, 64), (2, 64, 2, 3), (1, 5000, 1300, 16)])
+def test_reference_interpolate_kernels_equal_oracle_and_sg4d(cuda, ref, b, n, m, c):
+    """three_nn / three_interpolate (+grad): the reference's kernels vs the C oracle vs libsg4d.so"""
+    from sg4d.pointnet2_ops import _ext
+    g = torch.Generator().manual_seed(b + n + m)
+    unknown, known = torch.rand(b, n, 3, generator=g), torch.rand(b, m, 3, generator=g)
+    if m > 8:
+        known[0, 7] = known[0, 3]                               # exact distance ties
+    rd, ri = ref.three_nn(unknown.to(cuda), known.to(cuda))
+    od, oi = ora.three_nn(unknown, known)
+    sd, si = _ext.three_nn(unknown.to(cuda), known.to(cuda))
+    np.testing.assert_array_equal(ri.cpu().numpy(), oi.numpy())
+    np.testing.assert_array_equal(si.cpu().numpy(), oi.numpy())
+    np.testing.assert_array_equal(rd.cpu().numpy(), od.numpy())
+    np.testing.assert_array_equal(sd.cpu().numpy(), od.numpy())
+    feats = torch.randn(b, c, m, generator=g)
+    w = torch.rand(b, n, 3, generator=g)
+    r_out = ref.three_interpolate(feats.to(cuda), ri, w.to(cuda)).cpu()
+    np.testing.assert_array_equal(ora.three_interpolate(feats, oi, w).numpy(), r_out.numpy())
+    np.testing.assert_array_equal(_ext.three_interpolate(feats.to(cuda), si, w.to(cuda)).cpu().numpy(), r_out.numpy())
+    go = torch.randn(b, c, n, generator=g)
+    r_g = ref.three_interpolate_grad(go.to(cuda), ri, w.to(cuda), m).cpu()
+    torch.testing.assert_close(ora.three_interpolate_grad(go, oi, w, m), r_g, rtol=1e-5, atol=2e-5)   # atomics order
+    torch.testing.assert_close(_ext.three_interpolate_grad(go.to(cuda), si, w.to(cuda), m).cpu(), r_g, rtol=1e-5, atol=2e-5)

@@ -59,7 +59,7 @@ def test_cpu_tensors_are_rejected_like_the_reference():
         _ext.furthest_point_sampling(torch.rand(1, 3, 16).transpose(1, 2), 4)
     with pytest.raises(RuntimeError, match="int tensor"):
         _ext.gather_points(torch.rand(1, 3, 16), torch.zeros(1, 4, dtype=torch.int64))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="CPU not supported"):
         _ext.three_nn(xyz, xyz)
 
 

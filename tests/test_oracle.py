@@ -139,3 +139,29 @@ def test_model_fixture(golden_dir):
         eo = model_ref.forward(sd_eval, batch, training=False, dropout=False)
     np.testing.assert_allclose(eo[0].numpy(), fx["eval_obj_cls"], rtol=0, atol=1e-5)
     np.testing.assert_allclose(eo[1].numpy(), fx["eval_rel_cls"], rtol=0, atol=1e-5)
+
+
+def test_three_nn_and_interpolate_restatement():
+    """the FP-module ops: oracle vs plain torch on small clouds"""
+    from oracle import pn2_ext_cpu as ora
+    g = torch.Generator().manual_seed(11)
+    unknown, known = torch.rand(2, 50, 3, generator=g), torch.rand(2, 17, 3, generator=g)
+    known[0, 5] = known[0, 2]                                  # exact tie: the lower index comes first
+    dist2, idx = ora.three_nn(unknown, known)
+    d = ((unknown[:, :, None, :] - known[:, None, :, :]) ** 2).sum(-1)
+    want_d, want_i = torch.sort(d, dim=2, stable=True)
+    assert torch.equal(idx.long(), want_i[:, :, :3])
+    torch.testing.assert_close(dist2, want_d[:, :, :3], rtol=1e-6, atol=1e-7)
+    few = ora.three_nn(unknown, known[:, :2].contiguous())     # m < 3: missing slots are index 0 / +inf
+    assert torch.isinf(few[0][:, :, 2]).all() and int(few[1][:, :, 2].abs().sum()) == 0
+    feats = torch.randn(2, 4, 17, generator=g)
+    w = torch.rand(2, 50, 3, generator=g)
+    out = ora.three_interpolate(feats, idx, w)
+    gathered = torch.gather(feats[:, :, None, :].expand(-1, -1, 50, -1), 3, idx.long()[:, None].expand(-1, 4, -1, -1))
+    torch.testing.assert_close(out, (gathered * w[:, None]).sum(-1), rtol=1e-6, atol=1e-6)
+    go = torch.randn(2, 4, 50, generator=g)
+    grad = ora.three_interpolate_grad(go, idx, w, 17)
+    f2 = feats.clone().requires_grad_(True)
+    g2 = torch.gather(f2[:, :, None, :].expand(-1, -1, 50, -1), 3, idx.long()[:, None].expand(-1, 4, -1, -1))
+    ((g2 * w[:, None]).sum(-1) * go).sum().backward()
+    torch.testing.assert_close(grad, f2.grad, rtol=1e-5, atol=1e-5)
