@@ -151,13 +151,15 @@ struct RowGemmArgs {
 
 template <int N>
 struct RowSmem {
+    static constexpr int kStg = (N == 64) ? 3 : 2;          // smem stages: as many as fit beside the C tile
     static constexpr int kABytes = kTileM * 128;            // one hi or lo A tile
     static constexpr int kWBytes = N * 128;                 // one hi or lo W tile
     static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
     static constexpr int kCStride = N + 4;                  // padded fp32 row stride of the staged C tile
     static constexpr int kCBytes = kTileM * kCStride * 4;
     static constexpr int kConst = 3 * 256 * 4;              // prologue constants s, t, p
-    static constexpr int kTotal = 1024 + kStages * kStageBytes + kCBytes + kConst + 128;
+    static constexpr int stages(int pmode) { return pmode == 2 ? 2 : kStg; }   // PMODE 2 gathers through L1: keep it large
+    static constexpr int total(int pmode) { return 1024 + stages(pmode) * kStageBytes + kCBytes + kConst + 128; }
 };
 
 // PT = producer threads: 256, or 512 for layers with many k-blocks per tile (K >= 128), which are producer-bound
@@ -165,13 +167,14 @@ template <int N, int PMODE, int EMODE, int PT>
 __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowGemmArgs p) {
     constexpr int kProdThreads = PT, kProdWarps = PT / 32, kProdRows = kTileM * 8 / PT, kMlpThreads = PT + 32 + kEpiThreads;
     using SM = RowSmem<N>;
+    constexpr int kStages = SM::stages(PMODE);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 1024-byte aligned (swizzle atoms)
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
     float *Cs = reinterpret_cast<float *>(smem + kStages * SM::kStageBytes);
     float *s_s = reinterpret_cast<float *>(smem + kStages * SM::kStageBytes + SM::kCBytes);
     float *s_t = s_s + 256, *s_p = s_t + 256;
-    __shared__ __align__(8) uint64_t s_bar[2 * kStages + 4];
+    __shared__ __align__(8) uint64_t s_bar[2 * 4 + 4];
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -497,24 +500,28 @@ __device__ __forceinline__ uint32_t mn_b32_offset(int r, int c4) {
 
 template <int N>
 struct WgSmem {
+    static constexpr int kStg = N <= 32 ? 5 : (N <= 64 ? 4 : (N <= 128 ? 3 : 2));   // smem stages that fit in 227 KB
     static constexpr int kPBytes = 4 * 4096;                // 4 chunks of 32 channels x (32 k-lines x 128 B)
     static constexpr int kQBytes = (N / 32) * 4096;
     static constexpr int kStageBytes = 2 * kPBytes + 2 * kQBytes;
     static constexpr int kConst = 6 * 256 * 4;
-    static constexpr int kTotal = 1024 + kStages * kStageBytes + kConst + 128;
+    // pool_bwd_dw (PMODE 2) gathers dsel / garg through L1: it keeps 2 stages so that the L1 carve-out stays large
+    static constexpr int stages(int pmode) { return pmode == 2 ? 2 : kStg; }
+    static constexpr int total(int pmode) { return 1024 + stages(pmode) * kStageBytes + kConst + 128; }
 };
 
 template <int N, int PMODE, int QMODE>
 __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
     constexpr int kProdThreads = kProdThreadsT2, kProdWarps = kProdThreads / 32, kMlpThreads = kMlpThreadsT2;
     using SM = WgSmem<N>;
+    constexpr int kStages = SM::stages(PMODE);
     constexpr int kTmemCols = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
     float *cst = reinterpret_cast<float *>(smem + kStages * SM::kStageBytes);
     float *ps = cst, *pt = cst + 256, *pp = cst + 512, *qs = cst + 768, *qt = cst + 1024, *qp = cst + 1280;
-    __shared__ __align__(8) uint64_t s_bar[2 * kStages + 1];
+    __shared__ __align__(8) uint64_t s_bar[2 * 5 + 1];
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -733,7 +740,7 @@ static int launch_row(const RowGemmArgs &a0, int grid, cudaStream_t stream) {
     a.dbg_no_mma = getenv("SG4D_DBG_NOMMA") != nullptr, a.dbg_no_load = getenv("SG4D_DBG_NOLOAD") != nullptr;
     a.dbg_no_epi = getenv("SG4D_DBG_NOEPI") != nullptr;
     auto kern = row_gemm_kernel<N, PM, EM, PT>;
-    const int smem = RowSmem<N>::kTotal;
+    const int smem = RowSmem<N>::total(PM);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return status_of(e);
     kern<<<grid, PT + 32 + kEpiThreads, smem, stream>>>(a);
@@ -753,7 +760,7 @@ static int launch_wgrad(const WgradArgs &a0, int grid, cudaStream_t stream) {
     WgradArgs a = a0;
     a.dbg_no_mma = getenv("SG4D_DBG_NOMMA") != nullptr, a.dbg_no_load = getenv("SG4D_DBG_NOLOAD") != nullptr;
     auto kern = wgrad_kernel<N, PM, QM>;
-    const int smem = WgSmem<N>::kTotal;
+    const int smem = WgSmem<N>::total(PM);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return status_of(e);
     kern<<<grid, kMlpThreadsT2, smem, stream>>>(a);
