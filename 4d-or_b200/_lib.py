@@ -45,10 +45,11 @@ SIGNATURES = {
     "sg4d_pool_bwd_dw": [_i64, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "sg4d_inner_bwd_dx": [_i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "sg4d_inner_bwd_dw": [_i64, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "sg4d_pool_bwd_prologue": [_i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "sg4d_partial_sums": [_i, _i, _p, _p, _p],
 }
 OTHER_SYMBOLS = ["sg4d_abi_version", "sg4d_error_string", "sg4d_check_device", "sg4d_mlp_grid",
-                 "sg4d_weight_image_floats", "sg4d_wgrad_partial_floats", "sg4d_mlp_partial_doubles", "sg4d_spatial_index_bytes",
+                 "sg4d_weight_image_floats", "sg4d_wgrad_partial_floats", "sg4d_mlp_partial_doubles", "sg4d_pool_bwd_prologue_parts", "sg4d_spatial_index_bytes",
                  "sg4d_spatial_index_supported"]
 
 _lib = None
@@ -73,6 +74,7 @@ def load():
         lib.sg4d_mlp_partial_doubles.argtypes, lib.sg4d_mlp_partial_doubles.restype = [_i64], _i64
         lib.sg4d_weight_image_floats.argtypes, lib.sg4d_weight_image_floats.restype = [_i, _i], _i64
         lib.sg4d_wgrad_partial_floats.argtypes, lib.sg4d_wgrad_partial_floats.restype = [_i64, _i], _i64
+        lib.sg4d_pool_bwd_prologue_parts.argtypes, lib.sg4d_pool_bwd_prologue_parts.restype = [], _i
         lib.sg4d_spatial_index_bytes.argtypes, lib.sg4d_spatial_index_bytes.restype = [_i, _i], _i64
         lib.sg4d_spatial_index_supported.argtypes, lib.sg4d_spatial_index_supported.restype = [_i], _i
         if lib.sg4d_abi_version() != 1:

@@ -734,6 +734,49 @@ __global__ void partial_sum_kernel(int N, int nparts, const double *__restrict__
     out[N + c] = (float)q;
 }
 
+// Prologue of the pooled-layer backward (replaces six ATen elementwise / reduction launches over (G, N) tensors):
+//   dz = d_out * [out > 0];  dsel = dz * s2;  partial sums of  dz  and  dz * (gsel - m2) * i2  per channel.
+// blockDim = 256 = (N / 4 float4 columns) x (1024 / N rows per pass); fixed grid -> deterministic sums.
+__global__ void __launch_bounds__(256)
+pool_bwd_prologue_kernel(long long G, int N, int ldd, const float *__restrict__ d_out, const float *__restrict__ out,
+                         const float *__restrict__ gsel, const float *__restrict__ s2, const float *__restrict__ m2,
+                         const float *__restrict__ i2, float *__restrict__ dsel, double *__restrict__ partial) {
+    __shared__ double s_acc[256][8];
+    const int vec = N >> 2, rows_per_pass = 256 / vec;
+    const int c4 = threadIdx.x % vec, rl = threadIdx.x / vec;
+    const float4 sv = __ldg(reinterpret_cast<const float4 *>(s2) + c4), mv = __ldg(reinterpret_cast<const float4 *>(m2) + c4);
+    const float4 iv = __ldg(reinterpret_cast<const float4 *>(i2) + c4);
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int since = 0;
+    for (long long g = (long long)blockIdx.x * rows_per_pass + rl; g < G; g += (long long)gridDim.x * rows_per_pass) {
+        const float4 d = __ldg(reinterpret_cast<const float4 *>(d_out + g * ldd) + c4);
+        const float4 o = __ldg(reinterpret_cast<const float4 *>(out + g * N) + c4);
+        const float4 y = __ldg(reinterpret_cast<const float4 *>(gsel + g * N) + c4);
+        float4 z;
+        z.x = o.x > 0.f ? d.x : 0.f, z.y = o.y > 0.f ? d.y : 0.f, z.z = o.z > 0.f ? d.z : 0.f, z.w = o.w > 0.f ? d.w : 0.f;
+        reinterpret_cast<float4 *>(dsel + g * N)[c4] = make_float4(z.x * sv.x, z.y * sv.y, z.z * sv.z, z.w * sv.w);
+        a[0] += z.x, a[1] += z.y, a[2] += z.z, a[3] += z.w;
+        a[4] = fmaf(z.x, (y.x - mv.x) * iv.x, a[4]), a[5] = fmaf(z.y, (y.y - mv.y) * iv.y, a[5]);
+        a[6] = fmaf(z.z, (y.z - mv.z) * iv.z, a[6]), a[7] = fmaf(z.w, (y.w - mv.w) * iv.w, a[7]);
+        if (++since == 64) {   // fp32 over short runs, fp64 across them
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[u] += (double)a[u], a[u] = 0.f;
+            since = 0;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s_acc[threadIdx.x][u] = acc[u] + (double)a[u];
+    __syncthreads();
+    if (threadIdx.x < N) {   // column c = threadIdx.x: fold the row lanes in a fixed order
+        const int c = threadIdx.x, q = c >> 2, w = c & 3;
+        double t0 = 0.0, t1 = 0.0;
+        for (int r = 0; r < rows_per_pass; ++r) t0 += s_acc[r * vec + q][w], t1 += s_acc[r * vec + q][4 + w];
+        partial[((size_t)blockIdx.x * N + c) * 2 + 0] = t0;
+        partial[((size_t)blockIdx.x * N + c) * 2 + 1] = t1;
+    }
+}
+
 template <int N, int PM, int EM, int PT>
 static int launch_row(const RowGemmArgs &a0, int grid, cudaStream_t stream) {
     RowGemmArgs a = a0;
@@ -909,6 +952,19 @@ extern "C" int sg4d_bn_finalize(int n, int nparts, long long rows, const double 
     bn_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, nparts, rows, partial, gamma, beta, eps, momentum,
                                                                        running_mean, running_var, scale, shift, save_mean,
                                                                        save_invstd);
+    return SG4D_LAUNCH_CHECK();
+}
+
+extern "C" int sg4d_pool_bwd_prologue_parts(void) { return SG4D_NUM_SMS * 4; }
+
+extern "C" int sg4d_pool_bwd_prologue(long long groups, int n, int ldd, const float *d_out, const float *out,
+                                      const float *gsel, const float *s2, const float *m2, const float *i2, float *dsel,
+                                      double *partial, sg4d_stream_t stream) {
+    if (groups <= 0 || (n != 64 && n != 128) || ldd < n || (ldd & 3) || !d_out || !out || !gsel || !s2 || !m2 || !i2 || !dsel ||
+        !partial || (reinterpret_cast<uintptr_t>(d_out) & 15))
+        return SG4D_EINVAL;
+    pool_bwd_prologue_kernel<<<sg4d_pool_bwd_prologue_parts(), 256, 0, (cudaStream_t)stream>>>(groups, n, ldd, d_out, out, gsel,
+                                                                                              s2, m2, i2, dsel, partial);
     return SG4D_LAUNCH_CHECK();
 }
 

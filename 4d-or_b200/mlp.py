@@ -116,16 +116,25 @@ class _FusedSharedMLP(torch.autograd.Function):
         inv_r = 1.0 / rows
 
         # ---- layer 2: BatchNorm2 + ReLU + max-pool.  dY2 = dsel*[row is the pooled one] - (a2*y2 + b2)
-        dz = d_out * (out > 0)                                   # (G, n2) gradient at the selected rows
-        d_be2 = dz.sum(0)
-        d_g2 = (dz * ((gsel - m2) * i2)).sum(0)
+        # one fused pass over the pooled tensors: dz = d_out*[out > 0], dsel = dz*s2, and the two per-channel sums
+        groups = out.shape[0]
+        if d_out.stride(1) != 1 or (d_out.stride(0) & 3) or (d_out.data_ptr() & 15):
+            d_out = d_out.contiguous()
+        lib = _lib.load()
+        nparts = lib.sg4d_pool_bwd_prologue_parts() * n2
+        part2 = torch.empty(nparts * 2, dtype=torch.float64, device=dev)
+        dsel = torch.empty(groups, n2, dtype=torch.float32, device=dev)
+        _lib.call("sg4d_pool_bwd_prologue", x, groups, n2, d_out.stride(0), d_out.data_ptr(), out.data_ptr(), gsel.data_ptr(),
+                  s2.data_ptr(), m2.data_ptr(), i2.data_ptr(), dsel.data_ptr(), part2.data_ptr())
+        sums2 = torch.empty(2, n2, dtype=torch.float32, device=dev)
+        _lib.call("sg4d_partial_sums", x, n2, nparts, part2.data_ptr(), sums2.data_ptr())
+        d_be2, d_g2 = sums2[0], sums2[1]
         if batch2:
             a2 = s2 * d_g2 * i2 * inv_r
             b2 = s2 * d_be2 * inv_r - a2 * m2
         else:
             a2 = torch.zeros_like(s2)
             b2 = torch.zeros_like(s2)
-        dsel = (dz * s2).contiguous()
         em1 = (-m1 * i1).contiguous()
         dz1 = torch.empty(rows, n1, dtype=torch.float32, device=dev)
         part = torch.empty(_lib.load().sg4d_mlp_partial_doubles(rows), dtype=torch.float64, device=dev)

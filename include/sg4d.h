@@ -234,6 +234,15 @@ int sg4d_bn_finalize(int n, int nparts, long long rows, const double *partial, c
  * dY tensors are never materialised: the operand stagers evaluate the BatchNorm / ReLU / max-pool backward
  * formulas on the fly from y1, y2 and per-channel constants prepared on the host side (mlp.py).          */
 
+/* Prologue of the pooled-layer backward, one pass over the (groups, n) pooled tensors (n in {64, 128}):
+ *   dz = d_out .* [out > 0];  dsel = dz .* s2;  partial <- per-CTA fp64 sums of (dz, dz .* (gsel - m2) .* i2)
+ * d_out has row stride ldd (a slice of the concatenated MSG gradient), out / gsel / dsel are dense.  partial holds
+ * sg4d_pool_bwd_prologue_parts() * n pairs; sg4d_partial_sums(n, parts * n, ...) folds them into (d_beta2, d_gamma2). */
+int sg4d_pool_bwd_prologue_parts(void);
+int sg4d_pool_bwd_prologue(long long groups, int n, int ldd, const float *d_out, const float *out, const float *gsel,
+                           const float *s2, const float *m2, const float *i2, float *dsel, double *partial,
+                           sg4d_stream_t stream);
+
 /* dz1 = ((dY2) * W2) .* [y1*es + et > 0]   with  dY2[r,c] = dsel[r/group,c]*[r%group == garg[r/group,c]]
  *                                                          - (a2[c]*y2[r,c] + b2[c])
  * k = C2, n = C1; wimg_t = packed image of W2^T (n x k); also emits partial sums (sum dz1, sum dz1*yhat1),
