@@ -215,28 +215,30 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
         // of loads in flight per thread (memory-level parallelism: 128 threads x PD x 8 x 16 B per SM), so the HBM
         // latency of one chunk is hidden behind the transform + MMA of the previous ones.
         constexpr int PD = (PMODE <= 1) ? 4 : 2;      // modes 2/3 fetch two arrays per item: keep the ring within the register file
-        const long long my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-        const long long total = my_tiles * nkb;
+        // (tile, k-block) positions of the transform and of the loads PD chunks ahead of it are advanced incrementally
+        // (the first version divided a 64-bit chunk counter by nkb four times per chunk: ~100 instructions each)
         RawVec buf[PD][kProdRows];
-        auto issue = [&](long long q, RawVec (&dst)[kProdRows]) {
-            if (q < total && !p.dbg_no_load) {
-                const long long tile = blockIdx.x + (q / nkb) * gridDim.x;
-                const int kb = (int)(q % nkb);
+        long long tile_t = blockIdx.x, tile_i = blockIdx.x;
+        int kb_t = 0, kb_i = 0;
+        auto issue = [&](RawVec (&dst)[kProdRows]) {
+            if (tile_i < ntiles && !p.dbg_no_load) {
 #pragma unroll
-                for (int i = 0; i < kProdRows; ++i) op_load<PMODE>(p.op, tile * kTileM + r0 + (PT / 8) * i, p.R, kb * kKB + 4 * c, dst[i]);
+                for (int i = 0; i < kProdRows; ++i)
+                    op_load<PMODE>(p.op, tile_i * kTileM + r0 + (PT / 8) * i, p.R, kb_i * kKB + 4 * c, dst[i]);
             }
+            if (++kb_i == nkb) kb_i = 0, tile_i += gridDim.x;
         };
 #pragma unroll
-        for (int j = 0; j < PD; ++j) issue(j, buf[j]);
-        for (long long q0 = 0; q0 < total; q0 += PD) {
+        for (int j = 0; j < PD; ++j) issue(buf[j]);
+        uint32_t it = 0;
+        while (tile_t < ntiles) {
 #pragma unroll
             for (int j = 0; j < PD; ++j) {
-                const long long it = q0 + j;
-                if (it < total) {
-                    const long long tile = blockIdx.x + (it / nkb) * gridDim.x;
-                    const int kb = (int)(it % nkb);
+                if (tile_t < ntiles) {
+                    const long long tile = tile_t;
+                    const int kb = kb_t;
                     const int stage = (int)(it % kStages);
-                    mbar_wait_warp(lane, bar_empty + 8 * stage, (uint32_t)(((it / kStages) & 1) ^ 1));
+                    mbar_wait_warp(lane, bar_empty + 8 * stage, ((it / kStages) & 1u) ^ 1u);
                     uint8_t *st = smem + stage * SM::kStageBytes;
                     if (tid == 0 && !p.dbg_no_tma) {   // weight k-block: one bulk-TMA copy (hi tile followed by lo tile)
                         asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * stage),
@@ -259,14 +261,17 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                     tc::fence_proxy_async_smem();   // my smem writes -> visible to the tensor core (async proxy)
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(bar_full + 8 * stage);
-                    issue(it + PD, buf[j]);   // refill this ring slot
+                    issue(buf[j]);   // refill this ring slot
+                    if (++kb_t == nkb) kb_t = 0, tile_t += gridDim.x;
+                    ++it;
                 }
             }
         }
     } else if (warp == kProdWarps) {
         // =============================================================== MMA issuer
         constexpr uint32_t idesc = tc::umma_idesc_tf32(kTileM, N);
-        long long it = 0, ti = 0;
+        uint32_t it = 0;
+        long long ti = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
             const int acc = (int)(ti & 1);
             mbar_wait_warp<32>(lane, bar_tempty + 8 * acc, (uint32_t)(((ti >> 1) & 1) ^ 1));
