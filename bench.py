@@ -358,11 +358,51 @@ def main_sg4d(args):
             k["algorithmic_bytes"] = bts
             k["achieved_gbs"] = bts / (k["avg_ms"] * 1e-3) / 1e9
             k["hbm_frac"] = k["achieved_gbs"] / peak
-    if kernels:
-        top = next((k for k in kernels if "achieved_gbs" in k), kernels[0])
-        roof = {"bound": "hbm", "kernel": f"{top['call']}{tuple(top['args'])}", "achieved": top.get("achieved_gbs"),
-                "peak": peak, "unit": "GB/s", "frac": top.get("hbm_frac"), "traffic": None, "peak_source": peak_src,
-                "share_of_step": top["ms_per_step"] / table_ms_per_step}
+    # ---- roofline of the DOMINANT KERNEL: calls are grouped by the kernel that does their work; achieved =
+    #      algorithmic bytes of all its launches / their summed duration (= bytes per launch / average launch duration)
+    family = {"sg4d_linear_fwd": "row_gemm_kernel", "sg4d_pool_bwd_da": "row_gemm_kernel", "sg4d_inner_bwd_dx": "row_gemm_kernel",
+              "sg4d_pool_bwd_dw": "wgrad_kernel", "sg4d_inner_bwd_dw": "wgrad_kernel",
+              "sg4d_fps_indexed": "fps_indexed_kernel", "sg4d_fps_rows": "fps_onchip_kernel",
+              "sg4d_ball_query_rows_indexed": "ball_query_kernel+ball_query_indexed_kernel",
+              "sg4d_ball_query_rows": "ball_query_kernel", "sg4d_group_rows": "group_rows_kernel",
+              "sg4d_group_rows_grad": "group_rows_grad_kernel", "sg4d_spatial_index_build": "spatial_build_kernel"}
+    fam = {}
+    for k in kernels:
+        f = fam.setdefault(family.get(k["call"], k["call"]), {"ms": 0.0, "bytes": 0.0, "launches": 0.0, "calls": set()})
+        f["ms"] += k["ms_per_step"]
+        f["bytes"] += k.get("algorithmic_bytes", 0) * k["launches_per_step"]
+        f["launches"] += k["launches_per_step"]
+        f["calls"].add(k["call"])
+
+    def fam_roof(name, f):
+        ach = f["bytes"] / (f["ms"] * 1e-3) / 1e9 if f["ms"] > 0 and f["bytes"] > 0 else None
+        r = {"bound": "hbm", "kernel": name, "calls": sorted(f["calls"]), "launches_per_step": f["launches"],
+             "avg_launch_ms": f["ms"] / max(f["launches"], 1e-9), "algorithmic_bytes_per_launch": f["bytes"] / max(f["launches"], 1e-9),
+             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if ach else None, "traffic": None,
+             "peak_source": peak_src, "share_of_step": f["ms"] / table_ms_per_step}
+        tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        if os.path.exists(tp):   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
+            t = json.load(open(tp)).get("kernels", {}).get(name.split("+")[0])
+            if t and t.get("launches"):
+                r["traffic"] = t["dram_bytes"] / t["launches"]
+                r["traffic_source"] = "profiles/r01_ncu_traffic.json (ncu, same workload; average per launch)"
+        return r
+
+    if fam:
+        top_name = max(fam, key=lambda n: fam[n]["ms"])
+        roof = fam_roof(top_name, fam[top_name])
+        roof["others"] = {n: {"ms_per_step": f["ms"], "hbm_frac": (f["bytes"] / (f["ms"] * 1e-3) / 1e9 / peak) if f["bytes"] else None}
+                          for n, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]) if n != top_name}
+        # the pair BASELINE.json's north star singles out: ball query + group (SA1 and SA2 together)
+        bqg = {"ms": 0.0, "bytes": 0.0, "launches": 0.0, "calls": set()}
+        for n in ("ball_query_kernel+ball_query_indexed_kernel", "ball_query_kernel", "group_rows_kernel"):
+            if n in fam:
+                for key in ("ms", "bytes", "launches"):
+                    bqg[key] += fam[n][key]
+                bqg["calls"] |= fam[n]["calls"]
+        if bqg["ms"] > 0:
+            roof["ball_query_plus_group"] = {k2: v for k2, v in fam_roof("ball query + group", bqg).items()
+                                             if k2 in ("achieved", "frac", "unit", "share_of_step", "avg_launch_ms", "calls")}
 
     cpu = None
     if not args.no_cpu_baseline:
