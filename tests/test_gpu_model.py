@@ -150,7 +150,8 @@ def _assert_grad_close(name, got, ref, floor):
 
 
 @pytest.mark.parametrize("n_scenes,n_obj,n_pts,pairs,image", [(2, 3, 1500, "ordered", False), (3, 4, 1024, "unordered", True),
-                                                              (1, 12, 700, "unordered", False)])
+                                                              (1, 12, 700, "unordered", False),
+                                                              (1, 4, 12600, "unordered", False)])   # > 12288 points: spatial-index kernels
 def test_multi_scene_batch_against_oracle(cuda, n_scenes, n_obj, n_pts, pairs, image):
     """Concatenated scenes (the batched form the benchmark uses) vs the oracle on the same batch."""
     from sg4d import synthetic
