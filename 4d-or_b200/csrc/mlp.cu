@@ -705,14 +705,24 @@ pack_weight_kernel(int N, int K, int ldw, const float *__restrict__ W, float *__
 
 // BatchNorm batch statistics from the per-thread fp64 partials -> scale/shift (+ saved mean / invstd, running
 // statistics update with momentum and the unbiased variance, nn.BatchNorm2d semantics).
+// one warp per channel: lanes stride over the partials, fixed-order shuffle tree (deterministic)
+__device__ __forceinline__ void warp_sum_pairs(int c, int N, int nparts, const double *__restrict__ partial, double &s, double &q) {
+    const int lane = threadIdx.x & 31;
+    s = 0.0, q = 0.0;
+    for (int i = c + lane * N; i < nparts; i += 32 * N) s += partial[2 * (size_t)i], q += partial[2 * (size_t)i + 1];   // threads e with e % N == c
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o), q += __shfl_xor_sync(0xffffffffu, q, o);
+}
+
 __global__ void bn_finalize_kernel(int N, int nparts, long long R, const double *__restrict__ partial,
                                    const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
                                    float momentum, float *running_mean, float *running_var, float *scale, float *shift,
                                    float *save_mean, float *save_invstd) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c >= N) return;
-    double s = 0.0, q = 0.0;
-    for (int i = c; i < nparts; i += N) s += partial[2 * (size_t)i], q += partial[2 * (size_t)i + 1];   // threads e with e % N == c
+    double s, q;
+    warp_sum_pairs(c, N, nparts, partial, s, q);
+    if (threadIdx.x & 31) return;
     const double mean = s / (double)R;
     double var = q / (double)R - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -731,10 +741,11 @@ __global__ void bn_finalize_kernel(int N, int nparts, long long R, const double 
 
 // sums of the fp64 partial pairs per channel: out[0][c] = sum of first components, out[1][c] = second
 __global__ void partial_sum_kernel(int N, int nparts, const double *__restrict__ partial, float *__restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c >= N) return;
-    double s = 0.0, q = 0.0;
-    for (int i = c; i < nparts; i += N) s += partial[2 * (size_t)i], q += partial[2 * (size_t)i + 1];
+    double s, q;
+    warp_sum_pairs(c, N, nparts, partial, s, q);
+    if (threadIdx.x & 31) return;
     out[c] = (float)s;
     out[N + c] = (float)q;
 }
@@ -954,7 +965,7 @@ extern "C" int sg4d_bn_finalize(int n, int nparts, long long rows, const double 
                                 float *scale, float *shift, float *save_mean, float *save_invstd, sg4d_stream_t stream) {
     if (n <= 0 || nparts <= 0 || rows <= 0 || !partial || !gamma || !beta || !scale || !shift || !save_mean || !save_invstd)
         return SG4D_EINVAL;
-    bn_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, nparts, rows, partial, gamma, beta, eps, momentum,
+    bn_finalize_kernel<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(n, nparts, rows, partial, gamma, beta, eps, momentum,
                                                                        running_mean, running_var, scale, shift, save_mean,
                                                                        save_invstd);
     return SG4D_LAUNCH_CHECK();
@@ -975,6 +986,6 @@ extern "C" int sg4d_pool_bwd_prologue(long long groups, int n, int ldd, const fl
 
 extern "C" int sg4d_partial_sums(int n, int nparts, const double *partial, float *out, sg4d_stream_t stream) {
     if (n <= 0 || nparts <= 0 || !partial || !out) return SG4D_EINVAL;
-    partial_sum_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, nparts, partial, out);
+    partial_sum_kernel<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(n, nparts, partial, out);
     return SG4D_LAUNCH_CHECK();
 }
