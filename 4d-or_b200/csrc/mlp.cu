@@ -515,7 +515,9 @@ struct WgSmem {
     static constexpr int total(int pmode) { return 1024 + stages(pmode) * kStageBytes + kConst + 128; }
 };
 
-template <int N, int PMODE, int QMODE>
+// MV = valid channels of P (64 or 128): with 64 the upper half of the P tiles is zeroed once and never rewritten, so
+// the producers only transform the 16 valid float4 columns of each row
+template <int N, int PMODE, int QMODE, int MV>
 __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
     constexpr int kProdThreads = kProdThreadsT2, kProdWarps = kProdThreads / 32, kMlpThreads = kMlpThreadsT2;
     using SM = WgSmem<N>;
@@ -565,14 +567,25 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
         constexpr int kQVec = N / 4;                    // float4 per Q row
         constexpr int kQItems = (32 * kQVec + kProdThreads - 1) / kProdThreads;
         constexpr int PD = (N > 128) ? 1 : 2;           // k-blocks of loads in flight per thread (register ring, no spills)
-        constexpr int kPItems = 32 * 32 / kProdThreads;   // float4 of the P slab per thread
-        const int pc4 = tid & 31, pr0 = tid >> 5;       // P: my float4 column, rows pr0 + kProdWarps*i
+        constexpr int kPVec = MV / 4;                   // valid float4 per P row
+        constexpr int kPItems = 32 * kPVec / kProdThreads;   // float4 of the P slab per thread
         RawVec pv[PD][kPItems], qv[PD][kQItems];
+        if (MV < 128) {   // channels MV..127 of every P tile (hi and lo, all stages) stay zero for the whole kernel
+            constexpr int kZero = (4 - MV / 32) * 4096;
+            for (int s2 = 0; s2 < kStages; ++s2)
+                for (int t = 0; t < 2; ++t) {
+                    uint8_t *zb = smem + s2 * SM::kStageBytes + t * SM::kPBytes + (MV / 32) * 4096;
+                    for (int o = tid * 16; o < kZero; o += kProdThreads * 16) *reinterpret_cast<float4 *>(zb + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+        }
         auto issue = [&](long long kbk, RawVec (&pd)[kPItems], RawVec (&qd)[kQItems]) {
             if (kbk < nkb_total && !p.dbg_no_load) {
                 const long long row_base = t_beg * kTileM + kbk * kKB;
 #pragma unroll
-                for (int i = 0; i < kPItems; ++i) op_load<PMODE>(p.P, row_base + pr0 + kProdWarps * i, p.R, 4 * pc4, pd[i]);
+                for (int i = 0; i < kPItems; ++i) {
+                    const int item = tid + kProdThreads * i;
+                    op_load<PMODE>(p.P, row_base + item / kPVec, p.R, 4 * (item % kPVec), pd[i]);
+                }
 #pragma unroll
                 for (int i = 0; i < kQItems; ++i) {
                     const int item = tid + kProdThreads * i;
@@ -594,7 +607,8 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
                     uint8_t *st = smem + stage * SM::kStageBytes;
 #pragma unroll
                     for (int i = 0; i < kPItems; ++i) {
-                        const int r = pr0 + kProdWarps * i;
+                        const int item = tid + kProdThreads * i;
+                        const int r = item / kPVec, pc4 = item % kPVec;
                         const float4 v = op_apply<PMODE>(p.P, pv[j][i], row_base + r, p.R, 4 * pc4, ps, pt, pp);
                         float4 hi, lo;
                         split4(v, hi, lo);
@@ -818,7 +832,7 @@ template <int N, int PM, int QM>
 static int launch_wgrad(const WgradArgs &a0, int grid, cudaStream_t stream) {
     WgradArgs a = a0;
     a.dbg_no_mma = getenv("SG4D_DBG_NOMMA") != nullptr, a.dbg_no_load = getenv("SG4D_DBG_NOLOAD") != nullptr;
-    auto kern = wgrad_kernel<N, PM, QM>;
+    auto kern = a.P.ncols <= 64 ? wgrad_kernel<N, PM, QM, 64> : wgrad_kernel<N, PM, QM, 128>;
     const int smem = WgSmem<N>::total(PM);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return status_of(e);
