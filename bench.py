@@ -29,6 +29,15 @@ import torch  # noqa: E402
 
 CLOUDS_PER_SCENE = 78  # 12 objects + 66 edges
 
+# stdout carries exactly ONE JSON line: everything else that native libraries print there (NCCL's version banner, ...)
+# is routed to stderr by pointing fd 1 at fd 2 for the duration of the run
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -110,8 +119,8 @@ def cpu_sample_batch(args, n_clouds):
     """A bounded sample of the workload for the CPU legs: n_clouds clouds of a scene in the scene's own
     object:edge proportion (12:66), GNN run on as many edges as there are edge clouds."""
     from sg4d import synthetic
-    n_obj = max(1, round(n_clouds * 12 / CLOUDS_PER_SCENE))
-    n_rel = max(1, n_clouds - n_obj)
+    n_obj = max(2, round(n_clouds * 12 / CLOUDS_PER_SCENE))   # BatchNorm1d over the nodes / edges needs >= 2 rows
+    n_rel = max(2, n_clouds - n_obj)
     gen = torch.Generator().manual_seed(4321)
     pr = args.points_rel or args.points
     obj = torch.stack([synthetic.make_cloud(gen, args.points, 6) for _ in range(n_obj)])
@@ -189,7 +198,7 @@ def main_reference(args):
                        "this is the oracle port of its arithmetic on the host cores, rank 0 only"},
             "cpu_baseline": desc,
             "e2e": {"value": value, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -420,7 +429,7 @@ def main_sg4d(args):
             "kernel_table": {"ms_per_step": table_ms_per_step, "own_kernel_ms_per_step": own_ms,
                              "note": "second pass of the same steps, one stream, CUDA events around every C-ABI call"},
             "kernels": kernels[:48]}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
