@@ -194,3 +194,35 @@ def test_ref_shapes_forward_runs(cuda):
     m.training_step(batch).backward()
     assert m.obj_encoder.backbone.SA_modules[0].mlps[0][0].weight.grad is not None
     assert m.obj_encoder.backbone.fc_layer[0].weight.grad is None
+
+
+def test_inference_epilogue_matches_oracle_triples(cuda, tmp_path):
+    """predict_step / infer_scans / scan_relations_<name>_<split>.json (SGP/main.py:92-115, model.py:157-177): the
+    triples are those of the oracle's arg-max over the same weights, 'none' filtered, in edge order"""
+    import json as _json
+    from sg4d import synthetic
+    from sg4d.model import dump_scan_relations, infer_scans
+    sd = weights.synth_state_dict(seed=3)
+    m = _model(cuda, sd, 0.1, False)
+    names = m.relationNames
+    scans, want = [], {}
+    for sid in (21, 22):
+        sc = synthetic.make_scene(sid, n_obj=5, n_points_obj=600, n_points_rel=700, pairs="ordered")
+        sc["objs_json"] = {i + 1: f"obj{i}" for i in range(5)}
+        with torch.no_grad():
+            outs = model_ref.forward(model_ref.clone_state(sd), sc, training=False, dropout=False)
+        rel = outs[1].detach()
+        top2 = rel.topk(2, dim=1).values
+        rels = []
+        for e, (a, b) in enumerate(sc["edge_indices"].t().tolist()):
+            r = int(rel[e].argmax())
+            if names[r] != "none":
+                rels.append([f"obj{a}", names[r], f"obj{b}"])
+        if float((top2[:, 0] - top2[:, 1]).min()) < 1e-3:      # a near-tie could flip under fp32 noise: skip that scan
+            continue
+        want[sc["scan_id"]] = rels
+        scans.append(synthetic.to_device(sc, cuda))
+    got = infer_scans(m, scans)
+    path = dump_scan_relations(got, "sg4d", "test", str(tmp_path))
+    assert path.endswith("scan_relations_sg4d_test.json")
+    assert _json.load(open(path)) == want
