@@ -114,20 +114,29 @@ def drain_timing():
     return out
 
 
+_FN = {}
+
+
 def call(name, ref, *args):
     """Invoke ``name`` on the current stream of ``ref``'s device."""
     global LAUNCH_COUNT
-    lib = load()
+    fn = _FN.get(name)
+    if fn is None:
+        fn = _FN[name] = getattr(load(), name)
+    dev = ref.device
+    if dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):      # rare: a tensor of another device than the current one
+            return call(name, ref, *args)
     LAUNCH_COUNT += 1
-    with torch.cuda.device(ref.device):
-        if _TIMING is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            _check(getattr(lib, name)(*args, stream_ptr(ref)), name)
-            e1.record()
-            _TIMING.append((name, tuple(a for a in args[:6] if isinstance(a, int) and a < (1 << 31)), e0, e1))
-        else:
-            _check(getattr(lib, name)(*args, stream_ptr(ref)), name)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    if _TIMING is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _check(fn(*args, stream), name)
+        e1.record()
+        _TIMING.append((name, tuple(a for a in args[:6] if isinstance(a, int) and a < (1 << 31)), e0, e1))
+    else:
+        _check(fn(*args, stream), name)
 
 
 def ptr(t):
