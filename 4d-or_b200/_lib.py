@@ -123,12 +123,14 @@ def call(name, ref, *args):
     fn = _FN.get(name)
     if fn is None:
         fn = _FN[name] = getattr(load(), name)
-    dev = ref.device
-    if dev.index is not None and dev.index != torch.cuda.current_device():
-        with torch.cuda.device(dev):      # rare: a tensor of another device than the current one
+    index = ref.device.index
+    if index is not None and index != torch._C._cuda_getDevice():
+        with torch.cuda.device(ref.device):      # rare: a tensor of another device than the current one
             return call(name, ref, *args)
     LAUNCH_COUNT += 1
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    # raw handle of torch's current stream on that device (what torch.cuda.current_stream().cuda_stream returns,
+    # without building a Stream object on every call)
+    stream = torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice() if index is None else index)
     if _TIMING is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

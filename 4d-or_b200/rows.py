@@ -146,11 +146,11 @@ class EdgeCSR:
         self.by_src = self._csr(src)
 
     def _csr(self, key):
-        order = torch.sort(key, stable=True)[1].to(torch.int32)
-        counts = torch.bincount(key, minlength=self.n_nodes)
-        ptr = torch.zeros(self.n_nodes + 1, dtype=torch.int32, device=key.device)
-        ptr[1:] = torch.cumsum(counts, 0)
-        return order.contiguous(), ptr
+        # sort + searchsorted: no device->host synchronisation (torch.bincount would need the maximum on the host)
+        sorted_key, order = torch.sort(key, stable=True)
+        bounds = torch.arange(self.n_nodes + 1, dtype=key.dtype, device=key.device)
+        ptr = torch.searchsorted(sorted_key, bounds).to(torch.int32)
+        return order.to(torch.int32).contiguous(), ptr
 
 
 def _segment_sum(src, col0, d, order_ptr, n_nodes, col1=None):
