@@ -113,3 +113,32 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"] == {"value": d["value"], "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["metric"] == "scenes/sec fwd+bwd" and "workload" in d["config"]
+
+
+def test_edge_csr_matches_bincount_reference():
+    """EdgeCSR (sort + searchsorted, no host sync) == the obvious bincount/cumsum construction, including nodes
+    without edges and an empty edge list"""
+    from sg4d.rows import EdgeCSR
+    g = torch.Generator().manual_seed(0)
+    for n_nodes, n_edges in [(7, 30), (12, 66), (5, 0), (3, 4)]:
+        ei = torch.randint(0, n_nodes, (2, n_edges), generator=g)
+        csr = EdgeCSR(ei, n_nodes)
+        for key, (order, ptr) in ((ei[1], csr.by_dst), (ei[0], csr.by_src)):
+            counts = torch.bincount(key, minlength=n_nodes)
+            want = torch.zeros(n_nodes + 1, dtype=torch.int64)
+            want[1:] = torch.cumsum(counts, 0)
+            assert ptr.dtype == torch.int32 and torch.equal(ptr.long(), want)
+            assert torch.equal(key[order.long()], torch.sort(key, stable=True)[0])
+            assert torch.equal(order.long(), torch.sort(key, stable=True)[1])          # stable: ascending edge id per node
+
+
+def test_spatial_index_workspace_contract():
+    """host-side entry points of the spatial index: supported range and workspace size (no GPU needed)"""
+    lib = sg4d._lib.load()
+    assert lib.sg4d_spatial_index_supported(1023) == 0 and lib.sg4d_spatial_index_supported(1024) == 1
+    assert lib.sg4d_spatial_index_supported(80000) == 1 and lib.sg4d_spatial_index_supported(6144 * 64 + 1) == 0
+    one, two = lib.sg4d_spatial_index_bytes(1, 80000), lib.sg4d_spatial_index_bytes(2, 80000)
+    assert one >= 80000 * 20 and one % 4 == 0 and two > one
+    per_cloud = two - one                       # one more cloud: its index + its todo list
+    assert per_cloud % 128 == 0 or (per_cloud - 4 * 1025) % 128 == 0
+    assert lib.sg4d_spatial_index_bytes(0, 80000) in (0, 128) and lib.sg4d_spatial_index_bytes(3, 0) == 0
