@@ -8,12 +8,13 @@ The directory is named ``4d-or_b200`` (not an importable identifier); import it 
   pointnet2_ops/   mirror of the reference's operator API (``_ext``, ``pointnet2_utils``, ``pointnet2_modules``)
   rows.py          point-major fused operators used by the model path
   model/           mirror of the reference's model API (``SGPNModelWrapper`` and its sub-modules)
-  parallel.py      scene-sharded data parallelism (one NCCL gradient all-reduce per step)
+  parallel.py      scene-sharded data parallelism (one NCCL gradient all-reduce per step), host->device prefetcher
+  trainer.py       fit loop with the reference's per-epoch checkpoints / resume (no Lightning needed)
   synthetic.py     synthetic scenes of the benchmark shapes
 """
 from . import _lib  # noqa: F401
 
-__all__ = ["_lib", "pointnet2_ops", "rows", "model", "parallel", "synthetic"]
+__all__ = ["_lib", "pointnet2_ops", "rows", "model", "parallel", "synthetic", "trainer"]
 
 
 def library_path():

@@ -1,0 +1,96 @@
+"""Minimal trainer with the checkpoint / resume behaviour of the reference's ``main.py`` train mode
+(SGP/main.py:24-33,47-66), for environments without pytorch-lightning:
+
+* ``model.configure_optimizers()`` (AdamW, lr = LR, weight_decay = W_DECAY; SGH/model/scene_graph_prediction_model.py:240-242),
+* one ``training_step`` per batch, ``validation_step`` over the validation batches after every epoch,
+* a checkpoint per epoch named ``epoch=<N>.ckpt`` under ``<log_dir>/checkpoints`` (``ModelCheckpoint(filename='{epoch}',
+  save_top_k=-1, every_n_epochs=1)``), holding Lightning's keys ``epoch``, ``global_step``, ``state_dict``,
+  ``optimizer_states`` -- a reference checkpoint's ``state_dict`` loads into the sg4d model and vice versa,
+* resume from the newest ``epoch=<N>.ckpt`` (``find_checkpoint_path``).
+
+Multi-GPU: pass a ``parallel.GradBucket``; the gradients are all-reduced (mean) once per step.  The reference's
+``precision=16`` autocast / GradScaler is not reproduced: sg4d computes in fp32 (3xTF32 on the tensor cores).
+"""
+import glob
+import os
+import re
+
+import torch
+
+
+def find_checkpoint_path(log_dir):
+    """Newest ``epoch=<N>.ckpt`` in ``<log_dir>/checkpoints`` or None (SGP/main.py:24-33)."""
+    best, best_epoch = None, -1
+    for p in glob.glob(os.path.join(log_dir, "checkpoints", "*.ckpt")):
+        m = re.search(r"=(\d+)\.ckpt$", os.path.basename(p))
+        if m and int(m.group(1)) > best_epoch:
+            best, best_epoch = p, int(m.group(1))
+    return best
+
+
+def save_checkpoint(path, model, optimizer, epoch, global_step):
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    torch.save({"epoch": epoch, "global_step": global_step, "state_dict": model.state_dict(),
+                "optimizer_states": [optimizer.state_dict()]}, path)
+
+
+def load_checkpoint(path, model, optimizer=None, map_location=None):
+    """Loads a checkpoint written by this trainer or by Lightning (same keys); a bare ``state_dict`` file (the
+    reference's paper weights, SGP/main.py:78) is accepted too.  Returns (epoch, global_step)."""
+    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    if "state_dict" not in ckpt:
+        model.load_state_dict(ckpt)
+        return -1, 0
+    model.load_state_dict(ckpt["state_dict"])
+    if optimizer is not None and ckpt.get("optimizer_states"):
+        optimizer.load_state_dict(ckpt["optimizer_states"][0])
+    return int(ckpt.get("epoch", -1)), int(ckpt.get("global_step", 0))
+
+
+def fit(model, train_batches, val_batches=None, max_epochs=1, log_dir=None, bucket=None, on_epoch_end=None):
+    """Trains ``model`` (anything with ``training_step`` / ``validation_step`` / ``configure_optimizers``).
+
+    ``train_batches`` / ``val_batches``: callables returning an iterable of batch dicts for one epoch (device
+    tensors), or plain iterables.  Returns a list of per-epoch dicts (mean train / val loss).
+    """
+    optimizer = model.configure_optimizers()
+    start_epoch, global_step = 0, 0
+    if log_dir is not None:
+        ckpt = find_checkpoint_path(log_dir)
+        if ckpt is not None:
+            last, global_step = load_checkpoint(ckpt, model, optimizer)
+            start_epoch = last + 1
+    history = []
+
+    def batches_of(src):
+        return src() if callable(src) else src
+
+    for epoch in range(start_epoch, max_epochs):
+        model.train()
+        tot, cnt = 0.0, 0
+        for i, batch in enumerate(batches_of(train_batches)):
+            if bucket is not None:
+                bucket.zero()
+            else:
+                optimizer.zero_grad(set_to_none=True)
+            loss = model.training_step(batch, i)
+            loss.backward()
+            if bucket is not None:
+                bucket.all_reduce_mean()
+            optimizer.step()
+            global_step += 1
+            tot, cnt = tot + float(loss.detach()), cnt + 1
+        rec = {"epoch": epoch, "train_loss": tot / max(cnt, 1), "global_step": global_step}
+        if val_batches is not None:
+            model.eval()
+            with torch.no_grad():
+                vt, vc = 0.0, 0
+                for i, batch in enumerate(batches_of(val_batches)):
+                    vt, vc = vt + float(model.validation_step(batch, i)), vc + 1
+            rec["val_loss"] = vt / max(vc, 1)
+        if log_dir is not None:
+            save_checkpoint(os.path.join(log_dir, "checkpoints", f"epoch={epoch}.ckpt"), model, optimizer, epoch, global_step)
+        if on_epoch_end is not None:
+            on_epoch_end(rec)
+        history.append(rec)
+    return history
