@@ -226,3 +226,25 @@ def test_inference_epilogue_matches_oracle_triples(cuda, tmp_path):
     path = dump_scan_relations(got, "sg4d", "test", str(tmp_path))
     assert path.endswith("scan_relations_sg4d_test.json")
     assert _json.load(open(path)) == want
+
+
+def test_trainer_fit_checkpoint_roundtrip(cuda, tmp_path):
+    """sg4d.trainer.fit on the real model: AdamW steps change the weights, the per-epoch checkpoint restores them into a
+    fresh model (same eval outputs), and a resumed run continues at the next epoch"""
+    from sg4d import synthetic, trainer
+    sd = weights.synth_state_dict(seed=4)
+    scenes = [synthetic.to_device(synthetic.make_scene(30 + i, n_obj=4, n_points_obj=600, n_points_rel=700), cuda) for i in range(2)]
+    m = _model(cuda, sd, 0.1)
+    before = m.gcn.gconvs[0].nn1[0].weight.detach().clone()
+    hist = trainer.fit(m, scenes, scenes[:1], max_epochs=2, log_dir=str(tmp_path))
+    assert [h["epoch"] for h in hist] == [0, 1] and all(torch.isfinite(torch.tensor(h["train_loss"])) for h in hist)
+    assert not torch.equal(before, m.gcn.gconvs[0].nn1[0].weight)
+    assert m.obj_encoder.backbone.fc_layer[0].weight.grad is None            # dead parameters stay untouched
+    m2 = _model(cuda, sd, 0.1)
+    assert trainer.load_checkpoint(trainer.find_checkpoint_path(str(tmp_path)), m2)[0] == 1
+    m.eval(), m2.eval()
+    with torch.no_grad():
+        a, b = m(scenes[0]), m2(scenes[0])
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    hist2 = trainer.fit(m2, scenes, None, max_epochs=3, log_dir=str(tmp_path))
+    assert [h["epoch"] for h in hist2] == [2]
