@@ -12,6 +12,9 @@ Outputs (tests/golden/):
   model_cfg1.npz         reference SGPNModelWrapper forward+loss+backward on a BASELINE config-1
                          shaped scene (4 objects, 6 edges, 2048 points), train-mode BN, dropout off,
                          plus an eval-mode forward
+  fp_module.npz          reference three_nn / three_interpolate (pointnet2_utils.py:104-195) and one reference
+                         PointnetFPModule forward/backward (pointnet2_modules.py:149-209); `--only fp` regenerates
+                         just this file
 Weights are never stored: both sides rebuild them with oracle/weights.synth_state_dict.
 """
 import json
@@ -46,9 +49,44 @@ def adversarial_clouds(seed, b, n):
     return xyz.contiguous()
 
 
+def fp_fixture(U, M):
+    """feature propagation: the reference's own Python wrappers + FP module on top of the C restatement"""
+    g = torch.Generator().manual_seed(31)
+    unknown, known = torch.rand(3, 300, 3, generator=g), torch.rand(3, 70, 3, generator=g)
+    known[0, 9] = known[0, 4]                                # exact distance ties
+    dist, idx = U.three_nn(unknown, known)
+    rec = 1.0 / (dist + 1e-8)
+    weight = rec / torch.sum(rec, dim=2, keepdim=True)
+    kf = torch.randn(3, 6, 70, generator=g).requires_grad_(True)
+    interp = U.three_interpolate(kf, idx, weight)
+    wi = torch.randn(interp.shape, generator=g)
+    (interp * wi).sum().backward()
+    fix = {"unknown": unknown, "known": known, "dist": dist, "idx": idx, "known_feats": kf.detach(), "weight": weight,
+           "interp": interp.detach(), "w_interp": wi, "d_known_feats": kf.grad.clone()}
+    torch.manual_seed(7)
+    fp = M.PointnetFPModule(mlp=[6 + 4, 16, 8])
+    shapes = {k: list(v.shape) for k, v in fp.state_dict().items()}
+    fp.load_state_dict(weights.synth_state_dict(shapes, seed=9))
+    fp.train()
+    uf = torch.randn(3, 4, 300, generator=g)
+    kf2 = kf.detach().clone().requires_grad_(True)
+    out = fp(unknown, known, uf, kf2)
+    wo = torch.randn(out.shape, generator=g)
+    (out * wo).sum().backward()
+    fix.update({"fp_shapes": json.dumps(shapes), "unknown_feats": uf, "fp_out": out.detach(), "w_out": wo,
+                "fp_d_known_feats": kf2.grad})
+    for k, p in fp.named_parameters():
+        fix["fp_grad." + k] = p.grad
+    np.savez_compressed(os.path.join(OUT, "fp_module.npz"), **{k: np.asarray(v) for k, v in fix.items()})
+
+
 def main():
     rh.install(ext)
     U, M = rh.ref_utils(), rh.ref_modules()
+    fp_fixture(U, M)
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "fp":
+        print("fp_module.npz written to", OUT)
+        return
 
     # ---- state_dict layout
     model = rh.build_ref_model()

@@ -321,6 +321,35 @@ def test_three_nn_and_interpolate_match_oracle(cuda, b, n, m, c):
                                ora.three_interpolate_grad(go, oi, w, m), rtol=1e-5, atol=2e-5)
 
 
+def test_fp_module_against_reference_fixture(cuda, golden_dir):
+    """three_nn / three_interpolate wrappers and PointnetFPModule vs outputs of the REFERENCE's own Python
+    (tests/golden/fp_module.npz, generated by tests/golden/make_golden.py through oracle/ref_harness.py)"""
+    import json
+    from oracle import weights
+    from sg4d.pointnet2_ops import pointnet2_utils as U
+    from sg4d.pointnet2_ops.pointnet2_modules import PointnetFPModule
+    fx = np.load(os.path.join(golden_dir, "fp_module.npz"))
+    unknown, known = torch.from_numpy(fx["unknown"]).to(cuda), torch.from_numpy(fx["known"]).to(cuda)
+    dist, idx = U.three_nn(unknown, known)
+    np.testing.assert_array_equal(idx.cpu().numpy(), fx["idx"])
+    np.testing.assert_allclose(dist.cpu().numpy(), fx["dist"], rtol=1e-6, atol=0)       # sqrt on the GPU vs the CPU
+    kf = torch.from_numpy(fx["known_feats"]).to(cuda).requires_grad_(True)
+    interp = U.three_interpolate(kf, idx, torch.from_numpy(fx["weight"]).to(cuda))
+    np.testing.assert_array_equal(interp.detach().cpu().numpy(), fx["interp"])
+    (interp * torch.from_numpy(fx["w_interp"]).to(cuda)).sum().backward()
+    np.testing.assert_allclose(kf.grad.cpu().numpy(), fx["d_known_feats"], rtol=1e-5, atol=2e-5)
+    fp = PointnetFPModule(mlp=[6 + 4, 16, 8])
+    fp.load_state_dict(weights.synth_state_dict(json.loads(str(fx["fp_shapes"])), seed=9))
+    fp.to(cuda).train()
+    kf2 = torch.from_numpy(fx["known_feats"]).to(cuda).requires_grad_(True)
+    out = fp(unknown, known, torch.from_numpy(fx["unknown_feats"]).to(cuda), kf2)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), fx["fp_out"], rtol=0, atol=1e-4)
+    (out * torch.from_numpy(fx["w_out"]).to(cuda)).sum().backward()
+    np.testing.assert_allclose(kf2.grad.cpu().numpy(), fx["fp_d_known_feats"], rtol=1e-3, atol=1e-4)
+    for k, p in fp.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), fx["fp_grad." + k], rtol=1e-3, atol=2e-4, err_msg=k)
+
+
 def test_fp_module_forward_backward(cuda):
     """PointnetFPModule (OPS/pointnet2_modules.py:149-209) on the sg4d ops vs the same module arithmetic in torch"""
     from sg4d.pointnet2_ops.pointnet2_modules import PointnetFPModule

@@ -165,3 +165,20 @@ def test_three_nn_and_interpolate_restatement():
     g2 = torch.gather(f2[:, :, None, :].expand(-1, -1, 50, -1), 3, idx.long()[:, None].expand(-1, 4, -1, -1))
     ((g2 * w[:, None]).sum(-1) * go).sum().backward()
     torch.testing.assert_close(grad, f2.grad, rtol=1e-5, atol=1e-5)
+
+
+def test_fp_fixture_from_reference_python(golden_dir):
+    """fp_module.npz was produced by the reference's own pointnet2_utils.three_nn / three_interpolate wrappers; the
+    oracle ext called directly must reproduce it (pins the restatement's argument order / sqrt / weight handling)"""
+    import os
+    import numpy as np
+    from oracle import pn2_ext_cpu as ora
+    fx = np.load(os.path.join(golden_dir, "fp_module.npz"))
+    unknown, known = torch.from_numpy(fx["unknown"]), torch.from_numpy(fx["known"])
+    dist2, idx = ora.three_nn(unknown, known)
+    np.testing.assert_array_equal(idx.numpy(), fx["idx"])
+    np.testing.assert_array_equal(torch.sqrt(dist2).numpy(), fx["dist"])
+    out = ora.three_interpolate(torch.from_numpy(fx["known_feats"]), idx, torch.from_numpy(fx["weight"]))
+    np.testing.assert_array_equal(out.numpy(), fx["interp"])
+    g = ora.three_interpolate_grad(torch.from_numpy(fx["w_interp"]), idx, torch.from_numpy(fx["weight"]), known.shape[1])
+    np.testing.assert_allclose(g.numpy(), fx["d_known_feats"], rtol=1e-6, atol=1e-6)
