@@ -179,6 +179,8 @@ group_rows_wide4_kernel(long long rows, int n, int m, int nsample, int c, int pt
 // indices followed by repeats of the first), then walk the hits in (j, k) order while each lane
 // accumulates c/32 channels with coalesced 128-byte reads of grad_out.
 constexpr int kGgWarps = 16;
+// V4: the feature columns are 16-byte aligned (gcol0, out_stride, c multiples of 4): lanes accumulate float4 columns
+template <bool V4>
 __global__ void __launch_bounds__(kGgWarps * 32)
 group_rows_grad_kernel(int n, int m, int nsample, int c, int out_stride, int gcol0, int slices, int accumulate,
                        const float *__restrict__ grad_out, const int32_t *__restrict__ idx,
@@ -198,10 +200,11 @@ group_rows_grad_kernel(int n, int m, int nsample, int c, int out_stride, int gco
     constexpr int kMaxChunk = 8;  // c <= 256
     const int per_slice = (n + slices - 1) / slices;
     const int i_end = min(n, (slice + 1) * per_slice);
+    const int c4 = c >> 2;
     for (int i = slice * per_slice + warp; i < i_end; i += kGgWarps) {
         float acc[kMaxChunk];
 #pragma unroll
-        for (int u = 0; u < kMaxChunk; ++u) acc[u] = 0.f;
+        for (int u = 0; u < kMaxChunk; ++u) acc[u] = 0.f;   // V4: acc[4v .. 4v+3] = float4 column lane + 32 v
         for (int j0 = 0; j0 < m; j0 += 32) {
             const int j = j0 + lane;
             int pos = -1, cj = 0;
@@ -232,10 +235,21 @@ group_rows_grad_kernel(int n, int m, int nsample, int c, int out_stride, int gco
                 int k = pp;
                 while (k < nsample) {
                     const float *gr = g + (size_t)k * out_stride;
+                    if (V4) {
 #pragma unroll
-                    for (int u = 0; u < kMaxChunk; ++u) {
-                        const int ch = lane + 32 * u;
-                        if (ch < c) acc[u] += __ldg(gr + ch);
+                        for (int v = 0; v < kMaxChunk / 4; ++v) {
+                            const int q4 = lane + 32 * v;
+                            if (q4 < c4) {
+                                const float4 t = __ldg(reinterpret_cast<const float4 *>(gr) + q4);
+                                acc[4 * v] += t.x, acc[4 * v + 1] += t.y, acc[4 * v + 2] += t.z, acc[4 * v + 3] += t.w;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < kMaxChunk; ++u) {
+                            const int ch = lane + 32 * u;
+                            if (ch < c) acc[u] += __ldg(gr + ch);
+                        }
                     }
                     if (pp != 0) break;
                     k = (k == pp) ? cc : k + 1;
@@ -243,10 +257,26 @@ group_rows_grad_kernel(int n, int m, int nsample, int c, int out_stride, int gco
             }
         }
         float *o = grad_feats + (size_t)i * c;
+        if (V4) {
 #pragma unroll
-        for (int u = 0; u < kMaxChunk; ++u) {
-            const int ch = lane + 32 * u;
-            if (ch < c) o[ch] = accumulate ? o[ch] + acc[u] : acc[u];
+            for (int v = 0; v < kMaxChunk / 4; ++v) {
+                const int q4 = lane + 32 * v;
+                if (q4 < c4) {
+                    float4 t = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+                    float4 *dst = reinterpret_cast<float4 *>(o) + q4;
+                    if (accumulate) {
+                        const float4 old = *dst;
+                        t.x += old.x, t.y += old.y, t.z += old.z, t.w += old.w;
+                    }
+                    *dst = t;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < kMaxChunk; ++u) {
+                const int ch = lane + 32 * u;
+                if (ch < c) o[ch] = accumulate ? o[ch] + acc[u] : acc[u];
+            }
         }
     }
 }
@@ -330,12 +360,18 @@ extern "C" int sg4d_group_rows_grad(int b, int n, int m, int nsample, int c, int
     if (b == 0) return SG4D_OK;
     const size_t smem = ((size_t)m * nsample + m) * sizeof(int32_t);
     if (smem > 200 * 1024) return SG4D_EINVAL;
-    cudaError_t e = cudaFuncSetAttribute(group_rows_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool v4 = !((c | out_stride | gcol0) & 3) && !((reinterpret_cast<uintptr_t>(grad_out) | reinterpret_cast<uintptr_t>(grad_feats)) & 15);
+    cudaError_t e = cudaFuncSetAttribute(v4 ? group_rows_grad_kernel<true> : group_rows_grad_kernel<false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return status_of(e);
     // enough CTAs to cover the chip a few times even for a handful of clouds
     int slices = 1;
     while ((long long)b * slices < 4LL * SG4D_NUM_SMS && slices * kGgWarps * 2 <= n) slices *= 2;
-    group_rows_grad_kernel<<<(unsigned)(b * slices), kGgWarps * 32, smem, (cudaStream_t)stream>>>(
-        n, m, nsample, c, out_stride, gcol0, slices, accumulate, grad_out, idx, cnt, grad_feats);
+    if (v4)
+        group_rows_grad_kernel<true><<<(unsigned)(b * slices), kGgWarps * 32, smem, (cudaStream_t)stream>>>(
+            n, m, nsample, c, out_stride, gcol0, slices, accumulate, grad_out, idx, cnt, grad_feats);
+    else
+        group_rows_grad_kernel<false><<<(unsigned)(b * slices), kGgWarps * 32, smem, (cudaStream_t)stream>>>(
+            n, m, nsample, c, out_stride, gcol0, slices, accumulate, grad_out, idx, cnt, grad_feats);
     return SG4D_LAUNCH_CHECK();
 }

@@ -317,17 +317,24 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
             const int acc = (int)(ti & 1);
             mbar_wait_warp<128>(lane, bar_tfull + 8 * acc, (uint32_t)((ti >> 1) & 1));
             tc::tc_fence_after_sync();
+            // two 32-column chunks per wait: the second tcgen05.ld overlaps the first one's latency
 #pragma unroll
-            for (int c2 = 0; c2 < N / 32 / (kEpiThreads / 128); ++c2) {
-                const int ch = (kEpiThreads / 128) * c2 + half;
-                uint32_t v[32];
+            for (int c2 = 0; c2 < N / 32 / (kEpiThreads / 128); c2 += 2) {
+                const int ch = (kEpiThreads / 128) * c2 + half, ch2 = ch + (kEpiThreads / 128);
+                uint32_t v[32], w[32];
                 tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N + ch * 32), v);
+                tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N + ch2 * 32), w);
                 tc::tmem_ld_wait();
                 float4 *dst = reinterpret_cast<float4 *>(Cs + row * SM::kCStride + ch * 32);
+                float4 *dst2 = reinterpret_cast<float4 *>(Cs + row * SM::kCStride + ch2 * 32);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    dst2[j] = make_float4(__uint_as_float(w[4 * j]), __uint_as_float(w[4 * j + 1]),
+                                          __uint_as_float(w[4 * j + 2]), __uint_as_float(w[4 * j + 3]));
             }
             tc::tc_fence_before_sync();
             __syncwarp();
