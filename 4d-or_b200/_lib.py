@@ -47,10 +47,18 @@ SIGNATURES = {
     "sg4d_inner_bwd_dw": [_i64, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "sg4d_pool_bwd_prologue": [_i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "sg4d_partial_sums": [_i, _i, _p, _p, _p],
+    "sg4d_sa_moments": [_i64] + [_i] * 7 + [_p] * 5 + [_p],
+    "sg4d_sa1_bn1": [_i, _i, _p, _p, _i, _p, _p, _f, _f, _p, _p, _i, _p, _p, _p, _p],
+    "sg4d_sa1_fwd": [_i64] + [_i] * 7 + [_p] * 6 + [_i] + [_p] * 6 + [_p],
+    "sg4d_sa1_bwd_da": [_i64] + [_i] * 7 + [_p] * 6 + [_i] + [_p] * 7 + [_p],
+    "sg4d_sa1_bwd_dw2": [_i64] + [_i] * 7 + [_p] * 6 + [_i] + [_p] * 7 + [_p],
+    "sg4d_sa1_bwd_finalize": [_i, _i64, _p, _p, _p, _i, _p, _i, _p, _i, _p, _p, _p],
+    "sg4d_linear_fwd_grouped": [_i64] + [_i] * 7 + [_p] * 4 + [_i] + [_p] * 3 + [_p],
+    "sg4d_inner_bwd_dw_grouped": [_i64] + [_i] * 7 + [_p] * 4 + [_i] + [_p] * 7 + [_i, _p],
 }
 OTHER_SYMBOLS = ["sg4d_abi_version", "sg4d_error_string", "sg4d_check_device", "sg4d_mlp_grid",
                  "sg4d_weight_image_floats", "sg4d_wgrad_partial_floats", "sg4d_mlp_partial_doubles", "sg4d_pool_bwd_prologue_parts", "sg4d_spatial_index_bytes",
-                 "sg4d_spatial_index_supported"]
+                 "sg4d_spatial_index_supported", "sg4d_sa_moments_parts", "sg4d_sa1_s1part_doubles"]
 
 _lib = None
 
@@ -77,6 +85,8 @@ def load():
         lib.sg4d_pool_bwd_prologue_parts.argtypes, lib.sg4d_pool_bwd_prologue_parts.restype = [], _i
         lib.sg4d_spatial_index_bytes.argtypes, lib.sg4d_spatial_index_bytes.restype = [_i, _i], _i64
         lib.sg4d_spatial_index_supported.argtypes, lib.sg4d_spatial_index_supported.restype = [_i], _i
+        lib.sg4d_sa_moments_parts.argtypes, lib.sg4d_sa_moments_parts.restype = [], _i
+        lib.sg4d_sa1_s1part_doubles.argtypes, lib.sg4d_sa1_s1part_doubles.restype = [_i64], _i64
         if lib.sg4d_abi_version() != 1:
             raise RuntimeError("libsg4d.so ABI version mismatch; rebuild it")
         _lib = lib

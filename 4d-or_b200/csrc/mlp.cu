@@ -52,6 +52,18 @@ constexpr int kMlpThreadsT2 = kProdThreadsT2 + 32 + 128;
 //   mode 1   P = relu(A * s + t)                              BatchNorm + ReLU of the previous layer
 //   mode 2   P = dsel[g] * [row % S == garg[g]] - (A * s + t)  dY of a pooled layer (A = Y; g = row / S)
 //   mode 3   P = A2 * p - (A * s + t)                          dY of an inner layer (A = Y, A2 = dZ)
+//   mode 4   P = relu(W1s * x(row) + t1)   the first layer of an SA1 scale RECOMPUTED from the gathered neighbour
+//            (x = [xyz - centre | feats | 0.. | 1], K <= 7): neither the grouped tensor nor y1 exist in memory
+//   mode 5   P = grouped row gathered on the fly: [feats(idx) (c) | xyz(idx) - centre (3) | 0-pad]   (SA2)
+// Grouped-row source of one SA scale (replaces the materialised output of sg4d_group_rows):
+// row r = (cloud * m + centre) * ns + slot, neighbour point = idx[r].
+struct GroupSrc {
+    const float *pts, *feats, *centers;   // pts (B,n,pstride) xyz in 0..2; feats (B,n,fstride); centers (B,m,3)
+    const int32_t *idx;                   // (B,m,ns)
+    int n, m, logns, pstride, fstride, foff, c;
+    const float *w1s, *t1;                // mode 4: (8, 64) BatchNorm-scaled first-layer weights (input-major), (64) shifts
+};
+
 struct Operand {
     const float *A;
     int lda;
@@ -62,6 +74,7 @@ struct Operand {
     const uint8_t *garg;
     int S, logS, ldsel;         // S = 1 << logS rows per group
     int ncols;                  // valid columns; beyond -> 0
+    GroupSrc g;                 // modes 4 / 5
 };
 
 struct RawVec {                 // what one thread fetches for 4 consecutive columns of one row
@@ -107,6 +120,52 @@ __device__ __forceinline__ float4 op_apply(const Operand &o, const RawVec &r, lo
     return v;
 }
 
+// ---- gather modes -----------------------------------------------------------------------------
+// x = [xyz(idx) - centre | feats(idx) (c <= 4) | 0.. | 1]: the reference's grouped row (grouping_operation on xyz,
+// `grouped_xyz -= new_xyz`, cat with the grouped features: OPS/pointnet2_utils.py:319-328) plus a constant 1 in the
+// last slot, which turns the per-channel sums of the backward pass into one more column of the same product.
+__device__ __forceinline__ void sa1_gather_row(const GroupSrc &g, long long row, bool ok, int i, float (&x)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = 0.f;
+    if (!ok) return;
+    const long long gi = row >> g.logns;
+    const long long cloud = gi / g.m;
+    const float *pp = g.pts + (cloud * g.n + i) * g.pstride;
+    const float *ff = g.feats + (cloud * g.n + i) * g.fstride + g.foff;
+    const float *qq = g.centers + gi * 3;
+    x[0] = __ldg(pp) - __ldg(qq);
+    x[1] = __ldg(pp + 1) - __ldg(qq + 1);
+    x[2] = __ldg(pp + 2) - __ldg(qq + 2);
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+        if (ch < g.c) x[3 + ch] = __ldg(ff + ch);
+    x[7] = 1.f;
+}
+// BatchNorm-folded first layer for 4 consecutive output channels: ((t + x0 w0) + x1 w1) + ... in THIS order everywhere
+// (forward producer, backward epilogue, weight-gradient producer), so that the recomputed activation and its ReLU
+// mask are bit-identical to what the forward pass fed into the second layer.
+__device__ __forceinline__ float4 sa1_y1bn(const float (&x)[8], const float4 (&w)[8], const float4 &t) {
+    float4 v = t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        v.x = __fmaf_rn(x[j], w[j].x, v.x), v.y = __fmaf_rn(x[j], w[j].y, v.y);
+        v.z = __fmaf_rn(x[j], w[j].z, v.z), v.w = __fmaf_rn(x[j], w[j].w, v.w);
+    }
+    return v;
+}
+// mode 5: 4 consecutive columns of the grouped row [feats (c, multiple of 4) | xyz - centre | 0-pad]
+__device__ __forceinline__ float4 sa2_gather4(const GroupSrc &g, long long row, bool ok, int col, int i) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!ok || col > g.c) return v;
+    const long long gi = row >> g.logns;
+    const long long cloud = gi / g.m;
+    if (col < g.c) return __ldg(reinterpret_cast<const float4 *>(g.feats + (cloud * g.n + i) * g.fstride + g.foff + col));
+    const float *pp = g.pts + (cloud * g.n + i) * g.pstride;
+    const float *qq = g.centers + gi * 3;
+    v.x = __ldg(pp) - __ldg(qq), v.y = __ldg(pp + 1) - __ldg(qq + 1), v.z = __ldg(pp + 2) - __ldg(qq + 2);
+    return v;
+}
+
 // One lane polls the mbarrier, the rest of the warp waits at the warp barrier: 32x fewer try_wait requests hit
 // the barrier unit (with every thread polling, the waits themselves were the top stall in the first ncu capture).
 // SLEEP_NS > 0: back off between polls.  The waiting warps share the four issue ports with the producers, and the
@@ -133,6 +192,9 @@ __device__ __forceinline__ void split4(const float4 &v, float4 &hi, float4 &lo) 
 //   EMODE 0  store D; stats (sum d, sum d^2); optional group max/min + arg            forward layers
 //   EMODE 1  v = d * [E*es + et > 0]; store v; stats (sum v, sum v * (E*ei + em))      dZ of the inner layer
 //   EMODE 2  store D into Y(:, ycol0 : ycol0+N) with row stride ldy; no stats           dX
+//   EMODE 3  SA1 single-pass backward (N = 64): dz1 = D * [y1bn(x) > 0] with the first layer recomputed from the
+//            gathered neighbour x; accumulates S1 = dz1^T [x | 1] (64 x 8, fp64 across tiles).  dz1 is never stored:
+//            d_beta1, d_gamma1 and dW1 are all linear in S1 and in the forward moments sum x x^T (sa1_bwd_finalize).
 struct RowGemmArgs {
     Operand op;
     long long R;
@@ -146,7 +208,8 @@ struct RowGemmArgs {
     uint8_t *garg;           // (R/S, N)
     const float *E;          // EMODE 1: (R, N) pre-activation of the layer whose ReLU is differentiated
     const float *es, *et, *ei, *em;   // (N) each
-    int dbg_no_tma, dbg_no_mma, dbg_no_load, dbg_no_epi;
+    double *s1part;          // EMODE 3: (gridDim.x, 64, 8) per-CTA partial of S1
+    int dbg_no_tma, dbg_no_mma, dbg_no_load, dbg_no_epi;   // ablation switches, honoured only in SG4D_DEBUG builds
 };
 
 template <int N>
@@ -159,10 +222,19 @@ struct RowSmem {
     static constexpr int kCBytes = kTileM * kCStride * 4;
     static constexpr int kConst = 3 * 256 * 4;              // prologue constants s, t, p
     static constexpr int stages(int pmode) { return pmode == 2 ? 2 : kStg; }   // PMODE 2 gathers through L1: keep it large
-    static constexpr int total(int pmode) { return 1024 + stages(pmode) * kStageBytes + kCBytes + kConst + 128; }
+    static constexpr int kXaBytes = kTileM * 8 * 4;         // EMODE 3: the tile's gathered rows [x | 1]
+    static constexpr int kSaccBytes = 32 * kEpiThreads * 8; // EMODE 3: fp64 accumulators, 32 per epilogue thread
+    static constexpr int extra(int emode) { return emode == 3 ? kXaBytes + kSaccBytes : 0; }
+    static constexpr int total(int pmode, int emode) { return 1024 + stages(pmode) * kStageBytes + kCBytes + kConst + extra(emode) + 128; }
 };
 
 // PT = producer threads: 256, or 512 for layers with many k-blocks per tile (K >= 128), which are producer-bound
+#ifdef SG4D_DEBUG
+#define SG4D_DBG(x) (x)
+#else
+#define SG4D_DBG(x) 0
+#endif
+
 template <int N, int PMODE, int EMODE, int PT>
 __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowGemmArgs p) {
     constexpr int kProdThreads = PT, kProdWarps = PT / 32, kProdRows = kTileM * 8 / PT, kMlpThreads = PT + 32 + kEpiThreads;
@@ -196,7 +268,10 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
         tc::mbar_fence_init();
     }
     if (warp == kProdWarps) tc::tmem_alloc(smem_u32(&s_tmem), 2 * N);
-    if (PMODE != 0)
+    if (PMODE == 4) {            // s_s[0..511] = W1s (input-major, 8 x 64), s_p[0..63] = t1
+        for (int k = tid; k < 512; k += kMlpThreads) s_s[k] = p.op.g.w1s[k];
+        for (int k = tid; k < 64; k += kMlpThreads) s_p[k] = p.op.g.t1[k];
+    } else if (PMODE != 0 && PMODE != 5)
         for (int k = tid; k < 256; k += kMlpThreads) {
             s_s[k] = k < K ? p.op.s[k] : 0.f;
             s_t[k] = k < K ? p.op.t[k] : 0.f;
@@ -211,22 +286,117 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
         // =============================================================== producers
         const int c = tid & 7;        // my 16-byte chunk (4 fp32 columns) of every k-block
         const int r0 = tid >> 3;      // my rows: r0 + 32*i
+        // one k-block of the A tile is complete: weights by bulk TMA (one thread), my stores visible to the async proxy
+        auto weights_tma = [&](int stage, int kb) {
+            if (tid == 0 && !SG4D_DBG(p.dbg_no_tma)) {   // weight k-block: one bulk-TMA copy (hi tile followed by lo tile)
+                uint8_t *st = smem + stage * SM::kStageBytes;
+                asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * stage),
+                             "r"(2u * SM::kWBytes)
+                             : "memory");
+                tc::bulk_g2s(smem_u32(st + 2 * SM::kABytes), p.wimg + (size_t)kb * (2 * SM::kWBytes / 4), 2u * SM::kWBytes,
+                             bar_full + 8 * stage);
+            }
+        };
+        auto put = [&](uint8_t *st, int r, const float4 &v) {
+            float4 hi, lo;
+            split4(v, hi, lo);
+            const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+            *reinterpret_cast<float4 *>(st + off) = hi;
+            *reinterpret_cast<float4 *>(st + SM::kABytes + off) = lo;
+        };
+        if constexpr (PMODE == 4) {
+            // SA1: the operand is the first layer's activation, recomputed from the gathered neighbour of every row
+            // (two dependent loads: idx two tiles ahead, the point one tile ahead).  K = 64 -> two k-blocks per tile.
+            const GroupSrc &g = p.op.g;
+            float xc[kProdRows][8], xn[kProdRows][8];
+            int ib[kProdRows];
+            auto load_idx = [&](long long tile, int (&dst)[kProdRows]) {
+#pragma unroll
+                for (int i = 0; i < kProdRows; ++i) {
+                    const long long row = tile * kTileM + r0 + (PT / 8) * i;
+                    dst[i] = (tile < ntiles && row < p.R) ? __ldg(g.idx + row) : 0;
+                }
+            };
+            auto gather = [&](long long tile, const int (&ix)[kProdRows], float (&x)[kProdRows][8]) {
+#pragma unroll
+                for (int i = 0; i < kProdRows; ++i) {
+                    const long long row = tile * kTileM + r0 + (PT / 8) * i;
+                    sa1_gather_row(g, row, tile < ntiles && row < p.R, ix[i], x[i]);
+                }
+            };
+            long long tile = blockIdx.x;
+            load_idx(tile, ib);
+            gather(tile, ib, xc);
+            load_idx(tile + gridDim.x, ib);
+            uint32_t it = 0;
+            for (; tile < ntiles; tile += gridDim.x) {
+                gather(tile + gridDim.x, ib, xn);
+                load_idx(tile + 2LL * gridDim.x, ib);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int stage = (int)(it % kStages);
+                    mbar_wait_warp(lane, bar_empty + 8 * stage, ((it / kStages) & 1u) ^ 1u);
+                    uint8_t *st = smem + stage * SM::kStageBytes;
+                    weights_tma(stage, kb);
+                    const int col = kb * kKB + 4 * c;
+                    float4 w[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) w[j] = *reinterpret_cast<const float4 *>(s_s + j * 64 + col);
+                    const float4 t = *reinterpret_cast<const float4 *>(s_p + col);
+#pragma unroll
+                    for (int i = 0; i < kProdRows; ++i) {
+                        const int r = r0 + (PT / 8) * i;
+                        float4 v = sa1_y1bn(xc[i], w, t);
+                        const bool ok = tile * kTileM + r < p.R;
+                        v.x = ok ? fmaxf(v.x, 0.f) : 0.f, v.y = ok ? fmaxf(v.y, 0.f) : 0.f;
+                        v.z = ok ? fmaxf(v.z, 0.f) : 0.f, v.w = ok ? fmaxf(v.w, 0.f) : 0.f;
+                        put(st, r, v);
+                    }
+                    tc::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(bar_full + 8 * stage);
+                }
+#pragma unroll
+                for (int i = 0; i < kProdRows; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) xc[i][j] = xn[i][j];
+            }
+        } else {
         // Flat sequence of chunks q = (my tile index, k-block).  A static ring of PD register buffers keeps PD chunks
         // of loads in flight per thread (memory-level parallelism: 128 threads x PD x 8 x 16 B per SM), so the HBM
         // latency of one chunk is hidden behind the transform + MMA of the previous ones.
-        constexpr int PD = (PMODE <= 1) ? 4 : 2;      // modes 2/3 fetch two arrays per item: keep the ring within the register file
+        constexpr int PD = (PMODE <= 1 || PMODE == 5) ? 4 : 2;      // modes 2/3 fetch two arrays per item: keep the ring within the register file
         // (tile, k-block) positions of the transform and of the loads PD chunks ahead of it are advanced incrementally
         // (the first version divided a 64-bit chunk counter by nkb four times per chunk: ~100 instructions each)
         RawVec buf[PD][kProdRows];
         long long tile_t = blockIdx.x, tile_i = blockIdx.x;
         int kb_t = 0, kb_i = 0;
-        auto issue = [&](RawVec (&dst)[kProdRows]) {
-            if (tile_i < ntiles && !p.dbg_no_load) {
+        // mode 5 (rows gathered on the fly): the neighbour indices of my rows, for the tile being loaded and the next one
+        int ix_cur[kProdRows], ix_nxt[kProdRows];
+        auto load_idx = [&](long long tile, int (&dst)[kProdRows]) {
 #pragma unroll
-                for (int i = 0; i < kProdRows; ++i)
-                    op_load<PMODE>(p.op, tile_i * kTileM + r0 + (PT / 8) * i, p.R, kb_i * kKB + 4 * c, dst[i]);
+            for (int i = 0; i < kProdRows; ++i) {
+                const long long row = tile * kTileM + r0 + (PT / 8) * i;
+                dst[i] = (tile < ntiles && row < p.R) ? __ldg(p.op.g.idx + row) : 0;
             }
-            if (++kb_i == nkb) kb_i = 0, tile_i += gridDim.x;
+        };
+        if (PMODE == 5) load_idx(tile_i, ix_cur), load_idx(tile_i + gridDim.x, ix_nxt);
+        auto issue = [&](RawVec (&dst)[kProdRows]) {
+            if (tile_i < ntiles && !SG4D_DBG(p.dbg_no_load)) {
+#pragma unroll
+                for (int i = 0; i < kProdRows; ++i) {
+                    const long long row = tile_i * kTileM + r0 + (PT / 8) * i;
+                    if constexpr (PMODE == 5) dst[i].a = sa2_gather4(p.op.g, row, row < p.R, kb_i * kKB + 4 * c, ix_cur[i]);
+                    else op_load<PMODE>(p.op, row, p.R, kb_i * kKB + 4 * c, dst[i]);
+                }
+            }
+            if (++kb_i == nkb) {
+                kb_i = 0, tile_i += gridDim.x;
+                if (PMODE == 5) {
+#pragma unroll
+                    for (int i = 0; i < kProdRows; ++i) ix_cur[i] = ix_nxt[i];
+                    load_idx(tile_i + gridDim.x, ix_nxt);
+                }
+            }
         };
 #pragma unroll
         for (int j = 0; j < PD; ++j) issue(buf[j]);
@@ -240,23 +410,12 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                     const int stage = (int)(it % kStages);
                     mbar_wait_warp(lane, bar_empty + 8 * stage, ((it / kStages) & 1u) ^ 1u);
                     uint8_t *st = smem + stage * SM::kStageBytes;
-                    if (tid == 0 && !p.dbg_no_tma) {   // weight k-block: one bulk-TMA copy (hi tile followed by lo tile)
-                        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * stage),
-                                     "r"(2u * SM::kWBytes)
-                                     : "memory");
-                        tc::bulk_g2s(smem_u32(st + 2 * SM::kABytes), p.wimg + (size_t)kb * (2 * SM::kWBytes / 4),
-                                     2u * SM::kWBytes, bar_full + 8 * stage);
-                    }
+                    weights_tma(stage, kb);
                     const int col = kb * kKB + 4 * c;
 #pragma unroll
                     for (int i = 0; i < kProdRows; ++i) {
                         const int r = r0 + (PT / 8) * i;
-                        const float4 v = op_apply<PMODE>(p.op, buf[j][i], tile * kTileM + r, p.R, col, s_s, s_t, s_p);
-                        float4 hi, lo;
-                        split4(v, hi, lo);
-                        const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
-                        *reinterpret_cast<float4 *>(st + off) = hi;
-                        *reinterpret_cast<float4 *>(st + SM::kABytes + off) = lo;
+                        put(st, r, op_apply<(PMODE == 5 ? 0 : PMODE)>(p.op, buf[j][i], tile * kTileM + r, p.R, col, s_s, s_t, s_p));
                     }
                     tc::fence_proxy_async_smem();   // my smem writes -> visible to the tensor core (async proxy)
                     __syncwarp();
@@ -266,6 +425,7 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                     ++it;
                 }
             }
+        }
         }
     } else if (warp == kProdWarps) {
         // =============================================================== MMA issuer
@@ -285,7 +445,7 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                     const uint32_t a_hi = smem_base + stage * SM::kStageBytes, a_lo = a_hi + SM::kABytes;
                     const uint32_t w_hi = a_hi + 2 * SM::kABytes, w_lo = w_hi + SM::kWBytes;
 #pragma unroll
-                    for (int ks = 0; ks < kKB / 8 && !p.dbg_no_mma; ++ks) {
+                    for (int ks = 0; ks < kKB / 8 && !SG4D_DBG(p.dbg_no_mma); ++ks) {
                         const uint64_t dah = tc::umma_desc_k_sw128(a_hi + ks * 32), dal = tc::umma_desc_k_sw128(a_lo + ks * 32);
                         const uint64_t dwh = tc::umma_desc_k_sw128(w_hi + ks * 32), dwl = tc::umma_desc_k_sw128(w_lo + ks * 32);
                         tc::umma_tf32(d_tmem, dal, dwh, idesc, (kb | ks) != 0);   // small terms first
@@ -312,9 +472,32 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
         bool want_max = true;
         if (EMODE == 0 && p.S > 0) want_max = __ldg(p.gamma + col) >= 0.f;
         double dacc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        // EMODE 3: thread (cg, rs) owns channels 4cg..4cg+3 and rows 16rs..16rs+15 of every tile
+        float *xa_s = reinterpret_cast<float *>(smem + kStages * SM::kStageBytes + SM::kCBytes + SM::kConst);
+        double *sacc = reinterpret_cast<double *>(smem + kStages * SM::kStageBytes + SM::kCBytes + SM::kConst + SM::kXaBytes);
+        const int cg = e & 15, rs = e >> 4;
+        float4 w1[8], t1v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float sa[32];
+        int since = 0, ixn = 0;
+        if constexpr (EMODE == 3) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w1[j] = __ldg(reinterpret_cast<const float4 *>(p.op.g.w1s + j * 64 + 4 * cg));
+            t1v = __ldg(reinterpret_cast<const float4 *>(p.op.g.t1 + 4 * cg));
+#pragma unroll
+            for (int u = 0; u < 32; ++u) sa[u] = 0.f, sacc[u * kEpiThreads + e] = 0.0;
+            const long long row = (long long)blockIdx.x * kTileM + e;
+            ixn = row < p.R ? __ldg(p.op.g.idx + row) : 0;
+        }
         long long ti = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
             const int acc = (int)(ti & 1);
+            float xrow[8];
+            if constexpr (EMODE == 3) {   // my row of this tile (one row per epilogue thread), issued before the wait
+                const long long row = tile * kTileM + e;
+                sa1_gather_row(p.op.g, row, row < p.R, ixn, xrow);
+                const long long rown = row + (long long)gridDim.x * kTileM;
+                ixn = rown < p.R ? __ldg(p.op.g.idx + rown) : 0;
+            }
             mbar_wait_warp<128>(lane, bar_tfull + 8 * acc, (uint32_t)((ti >> 1) & 1));
             tc::tc_fence_after_sync();
             // two 32-column chunks per wait: the second tcgen05.ld overlaps the first one's latency
@@ -339,13 +522,36 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
             tc::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(bar_tempty + 8 * acc);   // accumulator may be overwritten
+            if constexpr (EMODE == 3) {
+                *reinterpret_cast<float4 *>(xa_s + e * 8) = make_float4(xrow[0], xrow[1], xrow[2], xrow[3]);
+                *reinterpret_cast<float4 *>(xa_s + e * 8 + 4) = make_float4(xrow[4], xrow[5], xrow[6], xrow[7]);
+            }
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 
             const long long row0 = tile * kTileM;
-            const int nvalid = p.dbg_no_epi ? 0 : (int)min((long long)kTileM, p.R - row0);
+            const int nvalid = SG4D_DBG(p.dbg_no_epi) ? 0 : (int)min((long long)kTileM, p.R - row0);
             constexpr int kVecPerRow = N / 4;
             constexpr int kRowStep = kEpiThreads / kVecPerRow;   // rows between two float4 items of one thread
-            if (EMODE == 1) {
+            if constexpr (EMODE == 3) {
+                const int rend = min(16 * rs + 16, nvalid);
+                for (int r = 16 * rs; r < rend; ++r) {
+                    const float4 xa0 = *reinterpret_cast<const float4 *>(xa_s + r * 8), xa1 = *reinterpret_cast<const float4 *>(xa_s + r * 8 + 4);
+                    const float xa[8] = {xa0.x, xa0.y, xa0.z, xa0.w, xa1.x, xa1.y, xa1.z, xa1.w};
+                    float4 d = *reinterpret_cast<const float4 *>(Cs + r * SM::kCStride + 4 * cg);
+                    const float4 y = sa1_y1bn(xa, w1, t1v);
+                    d.x = y.x > 0.f ? d.x : 0.f, d.y = y.y > 0.f ? d.y : 0.f, d.z = y.z > 0.f ? d.z : 0.f, d.w = y.w > 0.f ? d.w : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        sa[4 * j + 0] = fmaf(d.x, xa[j], sa[4 * j + 0]), sa[4 * j + 1] = fmaf(d.y, xa[j], sa[4 * j + 1]);
+                        sa[4 * j + 2] = fmaf(d.z, xa[j], sa[4 * j + 2]), sa[4 * j + 3] = fmaf(d.w, xa[j], sa[4 * j + 3]);
+                    }
+                }
+                if (++since == 16) {   // fp32 over 256 rows per thread, fp64 across
+                    since = 0;
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) sacc[u * kEpiThreads + e] += (double)sa[u], sa[u] = 0.f;
+                }
+            } else if (EMODE == 1) {
                 // ReLU mask of the inner layer from its pre-activation E (one coalesced read of E), store of dz,
                 // and the two BatchNorm-backward reductions -- every thread owns 4 fixed columns in this pass
                 const int cc = (e % kVecPerRow) * 4;
@@ -452,7 +658,20 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // Cs is reused by the next tile
         }
-        if (EMODE == 0) {
+        if constexpr (EMODE == 3) {
+            // S1 partial of this CTA: fold the 8 row slices in a fixed order -> (64 channels, 8 inputs) fp64
+#pragma unroll
+            for (int u = 0; u < 32; ++u) sacc[u * kEpiThreads + e] += (double)sa[u];
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            if (rs == 0) {
+#pragma unroll
+                for (int u = 0; u < 32; ++u) {
+                    double t = 0.0;
+                    for (int q2 = 0; q2 < 8; ++q2) t += sacc[u * kEpiThreads + q2 * 16 + cg];
+                    p.s1part[((size_t)blockIdx.x * 64 + 4 * cg + (u & 3)) * 8 + (u >> 2)] = t;
+                }
+            }
+        } else if (EMODE == 0) {
             p.partial[((size_t)blockIdx.x * kEpiThreads + e) * 2 + 0] = dacc[0];
             p.partial[((size_t)blockIdx.x * kEpiThreads + e) * 2 + 1] = dacc[1];
         } else if (EMODE == 1) {
@@ -559,9 +778,14 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
         ps[k] = (PMODE != 0 && k < p.P.ncols) ? p.P.s[k] : 0.f;
         pt[k] = (PMODE != 0 && k < p.P.ncols) ? p.P.t[k] : 0.f;
         pp[k] = (PMODE == 3 && k < p.P.ncols) ? p.P.p[k] : 0.f;
-        qs[k] = (QMODE != 0 && k < p.Q.ncols) ? p.Q.s[k] : 0.f;
-        qt[k] = (QMODE != 0 && k < p.Q.ncols) ? p.Q.t[k] : 0.f;
-        qp[k] = 0.f;
+        if (QMODE == 4) {      // qs[0..511] (= qs | qt) = W1s (input-major, 8 x 64), qp[0..63] = t1
+            qs[k] = p.Q.g.w1s[k], qt[k] = p.Q.g.w1s[256 + k];
+            qp[k] = k < 64 ? p.Q.g.t1[k] : 0.f;
+        } else {
+            qs[k] = (QMODE == 1 && k < p.Q.ncols) ? p.Q.s[k] : 0.f;
+            qt[k] = (QMODE == 1 && k < p.Q.ncols) ? p.Q.t[k] : 0.f;
+            qp[k] = 0.f;
+        }
     }
     tc::tc_fence_before_sync();
     __syncthreads();
@@ -585,8 +809,15 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
                     for (int o = tid * 16; o < kZero; o += kProdThreads * 16) *reinterpret_cast<float4 *>(zb + o) = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
         }
+        // Q gathered on the fly (modes 4 / 5): qd[i].arg carries the neighbour index of the row this ring slot gathers
+        // next; it is loaded one ring round (PD k-blocks) before the gather that depends on it
+        auto q_row_idx = [&](long long kbk, int i) -> uint32_t {
+            const int item = tid + kProdThreads * i;
+            const long long row = t_beg * kTileM + kbk * kKB + item / kQVec;
+            return (kbk < nkb_total && item < 32 * kQVec && row < p.R) ? (uint32_t)__ldg(p.Q.g.idx + row) : 0u;
+        };
         auto issue = [&](long long kbk, RawVec (&pd)[kPItems], RawVec (&qd)[kQItems]) {
-            if (kbk < nkb_total && !p.dbg_no_load) {
+            if (kbk < nkb_total && !SG4D_DBG(p.dbg_no_load)) {
                 const long long row_base = t_beg * kTileM + kbk * kKB;
 #pragma unroll
                 for (int i = 0; i < kPItems; ++i) {
@@ -597,10 +828,30 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
                 for (int i = 0; i < kQItems; ++i) {
                     const int item = tid + kProdThreads * i;
                     const int r = item / kQVec, c4 = item % kQVec;
-                    if (item < 32 * kQVec) op_load<QMODE>(p.Q, row_base + r, p.R, 4 * c4, qd[i]);
+                    if (item < 32 * kQVec) {
+                        if constexpr (QMODE == 4) {
+                            float x[8];
+                            sa1_gather_row(p.Q.g, row_base + r, row_base + r < p.R, (int)qd[i].arg, x);
+                            qd[i].a = make_float4(x[0], x[1], x[2], x[3]), qd[i].a2 = make_float4(x[4], x[5], x[6], x[7]);
+                        } else if constexpr (QMODE == 5) {
+                            qd[i].a = sa2_gather4(p.Q.g, row_base + r, row_base + r < p.R, 4 * c4, (int)qd[i].arg);
+                        } else {
+                            op_load<QMODE>(p.Q, row_base + r, p.R, 4 * c4, qd[i]);
+                        }
+                    }
                 }
             }
+            if constexpr (QMODE == 4 || QMODE == 5) {
+#pragma unroll
+                for (int i = 0; i < kQItems; ++i) qd[i].arg = q_row_idx(kbk + PD, i);
+            }
         };
+        if constexpr (QMODE == 4 || QMODE == 5) {
+#pragma unroll
+            for (int j = 0; j < PD; ++j)
+#pragma unroll
+                for (int i = 0; i < kQItems; ++i) qv[j][i].arg = q_row_idx(j, i);
+        }
 #pragma unroll
         for (int j = 0; j < PD; ++j) issue(j, pv[j], qv[j]);
         for (long long k0 = 0; k0 < nkb_total; k0 += PD) {
@@ -628,7 +879,20 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
                         const int item = tid + kProdThreads * i;
                         if (item < 32 * kQVec) {
                             const int r = item / kQVec, c4 = item % kQVec;
-                            const float4 v = op_apply<QMODE>(p.Q, qv[j][i], row_base + r, p.R, 4 * c4, qs, qt, qp);
+                            float4 v;
+                            if constexpr (QMODE == 4) {     // relu(W1s x + t1), the second layer's input, recomputed
+                                const float x[8] = {qv[j][i].a.x, qv[j][i].a.y, qv[j][i].a.z, qv[j][i].a.w,
+                                                    qv[j][i].a2.x, qv[j][i].a2.y, qv[j][i].a2.z, qv[j][i].a2.w};
+                                float4 w[8];
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) w[u] = *reinterpret_cast<const float4 *>(qs + u * 64 + 4 * c4);
+                                v = sa1_y1bn(x, w, *reinterpret_cast<const float4 *>(qp + 4 * c4));
+                                const bool ok = row_base + r < p.R;
+                                v.x = ok ? fmaxf(v.x, 0.f) : 0.f, v.y = ok ? fmaxf(v.y, 0.f) : 0.f;
+                                v.z = ok ? fmaxf(v.z, 0.f) : 0.f, v.w = ok ? fmaxf(v.w, 0.f) : 0.f;
+                            } else {
+                                v = op_apply<(QMODE == 5 ? 0 : QMODE)>(p.Q, qv[j][i], row_base + r, p.R, 4 * c4, qs, qt, qp);
+                            }
                             float4 hi, lo;
                             split4(v, hi, lo);
                             const uint32_t off = mn_b32_offset(r, c4);
@@ -654,7 +918,7 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
                 const uint32_t p_hi = smem_base + stage * SM::kStageBytes, p_lo = p_hi + SM::kPBytes;
                 const uint32_t q_hi = p_hi + 2 * SM::kPBytes, q_lo = q_hi + SM::kQBytes;
 #pragma unroll
-                for (int ks = 0; ks < kKB / 8 && !p.dbg_no_mma; ++ks) {   // 8 rows = one 1024-byte atom per chunk
+                for (int ks = 0; ks < kKB / 8 && !SG4D_DBG(p.dbg_no_mma); ++ks) {   // 8 rows = one 1024-byte atom per chunk
                     const uint32_t ko = ks * p.d_kstep;
                     const uint64_t dph = umma_desc_mn(p_hi + ko, p.d_lbo, p.d_sbo, p.d_type), dpl = umma_desc_mn(p_lo + ko, p.d_lbo, p.d_sbo, p.d_type);
                     const uint64_t dqh = umma_desc_mn(q_hi + ko, p.d_lbo, p.d_sbo, p.d_type), dql = umma_desc_mn(q_lo + ko, p.d_lbo, p.d_sbo, p.d_type);
@@ -817,10 +1081,13 @@ pool_bwd_prologue_kernel(long long G, int N, int ldd, const float *__restrict__ 
 template <int N, int PM, int EM, int PT>
 static int launch_row(const RowGemmArgs &a0, int grid, cudaStream_t stream) {
     RowGemmArgs a = a0;
-    a.dbg_no_mma = getenv("SG4D_DBG_NOMMA") != nullptr, a.dbg_no_load = getenv("SG4D_DBG_NOLOAD") != nullptr;
-    a.dbg_no_epi = getenv("SG4D_DBG_NOEPI") != nullptr;
+#ifdef SG4D_DEBUG   // ablation switches exist only in debug builds (a stray variable must never change production numerics)
+    static const bool no_mma = getenv("SG4D_DBG_NOMMA") != nullptr, no_load = getenv("SG4D_DBG_NOLOAD") != nullptr;
+    static const bool no_epi = getenv("SG4D_DBG_NOEPI") != nullptr, no_tma = getenv("SG4D_DBG_NOTMA") != nullptr;
+    a.dbg_no_mma = no_mma, a.dbg_no_load = no_load, a.dbg_no_epi = no_epi, a.dbg_no_tma = no_tma;
+#endif
     auto kern = row_gemm_kernel<N, PM, EM, PT>;
-    const int smem = RowSmem<N>::total(PM);
+    const int smem = RowSmem<N>::total(PM, EM);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return status_of(e);
     kern<<<grid, PT + 32 + kEpiThreads, smem, stream>>>(a);
@@ -829,16 +1096,17 @@ static int launch_row(const RowGemmArgs &a0, int grid, cudaStream_t stream) {
 
 template <int PM, int EM>
 static int launch_row_n(int n, const RowGemmArgs &a, int grid, cudaStream_t stream) {
-    static const int force = getenv("SG4D_ROW_PT") ? atoi(getenv("SG4D_ROW_PT")) : 0;
-    const bool wide = force == 512;   // measured: 16 producer warps do not pay for T1 (80-register cap, epilogue-bound)
-    if (wide) return n == 128 ? launch_row<128, PM, EM, 512>(a, grid, stream) : launch_row<64, PM, EM, 512>(a, grid, stream);
+    // (measured in round 1: 16 producer warps do not pay for the row-tile kernels -- 80-register cap, epilogue-bound)
     return n == 128 ? launch_row<128, PM, EM, 256>(a, grid, stream) : launch_row<64, PM, EM, 256>(a, grid, stream);
 }
 
 template <int N, int PM, int QM>
 static int launch_wgrad(const WgradArgs &a0, int grid, cudaStream_t stream) {
     WgradArgs a = a0;
-    a.dbg_no_mma = getenv("SG4D_DBG_NOMMA") != nullptr, a.dbg_no_load = getenv("SG4D_DBG_NOLOAD") != nullptr;
+#ifdef SG4D_DEBUG
+    static const bool no_mma = getenv("SG4D_DBG_NOMMA") != nullptr, no_load = getenv("SG4D_DBG_NOLOAD") != nullptr;
+    a.dbg_no_mma = no_mma, a.dbg_no_load = no_load;
+#endif
     auto kern = a.P.ncols <= 64 ? wgrad_kernel<N, PM, QM, 64> : wgrad_kernel<N, PM, QM, 128>;
     const int smem = WgSmem<N>::total(PM);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -904,7 +1172,6 @@ extern "C" int sg4d_linear_fwd(long long rows, int k, int lda, int n, int group,
     args.R = rows, args.wimg = wimg, args.Y = y, args.ldy = n, args.ycol0 = 0, args.partial = partial;
     args.S = group, args.logS = ilog2(group), args.gamma = gamma, args.gsel = gsel, args.garg = garg;
     const int grid = mlp_grid(rows);
-    args.dbg_no_tma = getenv("SG4D_DBG_NOTMA") != nullptr;
     return scale ? launch_row_n<1, 0>(n, args, grid, (cudaStream_t)stream)
                  : launch_row_n<0, 0>(n, args, grid, (cudaStream_t)stream);
 }
@@ -1008,5 +1275,262 @@ extern "C" int sg4d_pool_bwd_prologue(long long groups, int n, int ldd, const fl
 extern "C" int sg4d_partial_sums(int n, int nparts, const double *partial, float *out, sg4d_stream_t stream) {
     if (n <= 0 || nparts <= 0 || !partial || !out) return SG4D_EINVAL;
     partial_sum_kernel<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(n, nparts, partial, out);
+    return SG4D_LAUNCH_CHECK();
+}
+
+// ================================================================================================
+// Fused set-abstraction scales: the grouped tensor is never materialised.
+//
+// SA1 (K = 3 + c <= 7 input channels, 64 first-layer channels, no gradient into the points):
+//   forward   sa_moments_kernel  -> M = sum over grouped rows of [x | 1][x | 1]^T (8 x 8, fp64).  The first layer is
+//                                   linear in x, so BatchNorm1's batch statistics follow from M alone:
+//                                   mean = W1 mu, E[y^2] = w^T (M / R) w  (sa1_bn1_kernel; also emits the
+//                                   BatchNorm-scaled weights W1s and shifts t1)
+//             row_gemm<N2, 4, 0> -> y2 = relu(W1s x + t1) W2^T with the first layer recomputed in the producers
+//                                   (8 FMAs per activation instead of a 256-byte HBM round trip per row),
+//                                   BatchNorm2 statistics + group max/min in the epilogue
+//   backward  row_gemm<64, 2, 3> -> dz1 = (dY2 W2) * [y1bn > 0] consumed in the epilogue: S1 = dz1^T [x | 1]
+//             wgrad<64, 2, 4>    -> dW2 = dY2^T relu(W1s x + t1), the second operand recomputed from the gather
+//             sa1_bwd_finalize   -> d_beta1 = S1[:,7], d_gamma1 = i1 (sum_j W1 S1 - m1 d_beta1),
+//                                   dW1 = p1 S1 - q1 (W1 M) - u1 (1^T x): every term is linear in S1 and M
+// SA2 (K = 195): row_gemm<128, 5, 0> and wgrad<224, 3, 5> gather the rows straight into the swizzled operand tiles.
+namespace sg4d {
+
+constexpr int kMomentParts = SG4D_NUM_SMS * 4;
+
+__global__ void __launch_bounds__(256) sa_moments_kernel(GroupSrc g, long long R, double *__restrict__ part) {
+    double acc[36];
+#pragma unroll
+    for (int u = 0; u < 36; ++u) acc[u] = 0.0;
+    for (long long row = blockIdx.x * 256LL + threadIdx.x; row < R; row += (long long)gridDim.x * 256) {
+        float x[8];
+        sa1_gather_row(g, row, true, __ldg(g.idx + row), x);
+        int u = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = i; j < 8; ++j, ++u) acc[u] = fma((double)x[i], (double)x[j], acc[u]);   // products are exact in fp64
+    }
+    __shared__ double s_part[8][36];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int u = 0; u < 36; ++u) {
+        double v = acc[u];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_part[warp][u] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 36) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += s_part[w][threadIdx.x];
+        part[(size_t)blockIdx.x * 36 + threadIdx.x] = v;
+    }
+}
+
+// one block of 64 threads.  moments (8 x 8, full symmetric) is kept for the backward pass.
+__global__ void sa1_bn1_kernel(int k, int nparts, const double *__restrict__ part, const float *__restrict__ w1, int ldw,
+                               const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float momentum,
+                               float *running_mean, float *running_var, int use_running, double *__restrict__ moments,
+                               float *__restrict__ stats, float *__restrict__ w1s) {
+    __shared__ double M[8][8];
+    const int t = threadIdx.x;
+    if (t < 36) {
+        double v = 0.0;
+        for (int q = 0; q < nparts; ++q) v += part[(size_t)q * 36 + t];
+        int i = 0, rem = t;
+        while (rem >= 8 - i) rem -= 8 - i, ++i;
+        const int j = i + rem;
+        M[i][j] = v, M[j][i] = v;
+    }
+    __syncthreads();
+    moments[t] = M[t >> 3][t & 7];
+    const double R = M[7][7];
+    double mean = 0.0, ey2 = 0.0;
+    for (int i = 0; i < k; ++i) {
+        const double wi = (double)w1[(size_t)t * ldw + i];
+        mean += wi * M[i][7];
+        for (int j = 0; j < k; ++j) ey2 += wi * (double)w1[(size_t)t * ldw + j] * M[i][j];
+    }
+    mean /= R, ey2 /= R;
+    double var = ey2 - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float invstd, meanf;
+    if (use_running) {
+        meanf = running_mean[t];
+        invstd = (float)(1.0 / sqrt((double)running_var[t] + (double)eps));
+    } else {
+        meanf = (float)mean;
+        invstd = (float)(1.0 / sqrt(var + (double)eps));
+        if (running_mean) {
+            const double unbiased = R > 1.0 ? var * R / (R - 1.0) : var;
+            running_mean[t] = (1.f - momentum) * running_mean[t] + momentum * meanf;
+            running_var[t] = (1.f - momentum) * running_var[t] + momentum * (float)unbiased;
+        }
+    }
+    const float sc = gamma[t] * invstd;
+    stats[t] = sc, stats[64 + t] = beta[t] - meanf * sc, stats[128 + t] = meanf, stats[192 + t] = invstd;
+    for (int j = 0; j < 8; ++j) w1s[j * 64 + t] = j < k ? __fmul_rn(sc, w1[(size_t)t * ldw + j]) : 0.f;
+}
+
+// one block of 512 threads: thread (c = t / 8, j = t % 8)
+__global__ void __launch_bounds__(512)
+sa1_bwd_finalize_kernel(int k, int nparts, const double *__restrict__ s1part, const double *__restrict__ moments,
+                        const float *__restrict__ w1, int ldw, const float *__restrict__ stats, int batch_stats,
+                        float *__restrict__ d_w1, int lddw, float *__restrict__ d_g1, float *__restrict__ d_be1) {
+    __shared__ double S[64][8];
+    const int t = threadIdx.x, c = t >> 3, j = t & 7;
+    double v = 0.0;
+    for (int q = 0; q < nparts; ++q) v += s1part[(size_t)q * 512 + t];
+    S[c][j] = v;
+    __syncthreads();
+    const double R = moments[63];
+    const double s1 = stats[c], m1 = stats[128 + c], i1 = stats[192 + c];
+    const double dbe = S[c][7];
+    double sdy = 0.0;
+    for (int i = 0; i < k; ++i) sdy += (double)w1[(size_t)c * ldw + i] * S[c][i];
+    const double dg = i1 * (sdy - m1 * dbe);
+    const double q1 = batch_stats ? s1 * dg * i1 / R : 0.0;
+    const double u1 = batch_stats ? s1 * dbe / R - q1 * m1 : 0.0;
+    if (j < k) {
+        double wm = 0.0;
+        for (int i = 0; i < k; ++i) wm += (double)w1[(size_t)c * ldw + i] * moments[i * 8 + j];
+        d_w1[(size_t)c * lddw + j] = (float)(s1 * S[c][j] - q1 * wm - u1 * moments[j * 8 + 7]);
+    }
+    if (j == 0) d_g1[c] = (float)dg, d_be1[c] = (float)dbe;
+}
+
+static bool fill_src(GroupSrc &g, long long rows, int n, int m, int ns, int pstride, int fstride, int foff, int c,
+                     const float *pts, const float *feats, const float *centers, const int32_t *idx) {
+    if (rows <= 0 || n <= 0 || m <= 0 || !pow2(ns) || ns > 128 || rows % ((long long)m * ns) || pstride < 3 || c < 0 || !pts ||
+        !centers || !idx || (c > 0 && (!feats || fstride < foff + c || foff < 0)))
+        return false;
+    g.pts = pts, g.feats = feats ? feats : pts, g.centers = centers, g.idx = idx;
+    g.n = n, g.m = m, g.logns = ilog2(ns), g.pstride = pstride, g.fstride = feats ? fstride : pstride, g.foff = foff, g.c = c;
+    g.w1s = nullptr, g.t1 = nullptr;
+    return true;
+}
+
+}  // namespace sg4d
+
+extern "C" int sg4d_sa_moments_parts(void) { return kMomentParts; }
+
+extern "C" int sg4d_sa_moments(long long rows, int n, int m, int ns, int pstride, int fstride, int foff, int c,
+                               const float *pts, const float *feats, const float *centers, const int32_t *idx,
+                               double *part, sg4d_stream_t stream) {
+    GroupSrc g;
+    if (!fill_src(g, rows, n, m, ns, pstride, fstride, foff, c, pts, feats, centers, idx) || c > 4 || !part) return SG4D_EINVAL;
+    sa_moments_kernel<<<kMomentParts, 256, 0, (cudaStream_t)stream>>>(g, rows, part);
+    return SG4D_LAUNCH_CHECK();
+}
+
+extern "C" int sg4d_sa1_bn1(int k, int nparts, const double *part, const float *w1, int ldw, const float *gamma,
+                            const float *beta, float eps, float momentum, float *running_mean, float *running_var,
+                            int use_running, double *moments, float *stats, float *w1s, sg4d_stream_t stream) {
+    if (k < 3 || k > 7 || nparts <= 0 || !part || !w1 || ldw < k || !gamma || !beta || !moments || !stats || !w1s ||
+        (use_running && (!running_mean || !running_var)))
+        return SG4D_EINVAL;
+    sa1_bn1_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(k, nparts, part, w1, ldw, gamma, beta, eps, momentum, running_mean,
+                                                      running_var, use_running, moments, stats, w1s);
+    return SG4D_LAUNCH_CHECK();
+}
+
+extern "C" int sg4d_sa1_fwd(long long rows, int n, int m, int ns, int pstride, int fstride, int foff, int c, const float *pts,
+                            const float *feats, const float *centers, const int32_t *idx, const float *w1s, const float *t1,
+                            int n2, const float *wimg2, float *y2, double *partial, const float *gamma2, float *gsel,
+                            uint8_t *garg, sg4d_stream_t stream) {
+    RowGemmArgs args{};
+    if (!fill_src(args.op.g, rows, n, m, ns, pstride, fstride, foff, c, pts, feats, centers, idx) || c > 4 || !w1s || !t1 ||
+        (n2 != 64 && n2 != 128) || !wimg2 || !y2 || !partial || !gamma2 || !gsel || !garg || ns < 8 ||
+        ns > kTileM / (kEpiThreads / n2))
+        return SG4D_EINVAL;
+    args.op.g.w1s = w1s, args.op.g.t1 = t1, args.op.ncols = 64;
+    args.R = rows, args.wimg = wimg2, args.Y = y2, args.ldy = n2, args.ycol0 = 0, args.partial = partial;
+    args.S = ns, args.logS = ilog2(ns), args.gamma = gamma2, args.gsel = gsel, args.garg = garg;
+    return launch_row_n<4, 0>(n2, args, mlp_grid(rows), (cudaStream_t)stream);
+}
+
+extern "C" long long sg4d_sa1_s1part_doubles(long long rows) { return (long long)mlp_grid(rows) * 512; }
+
+extern "C" int sg4d_sa1_bwd_da(long long rows, int n, int m, int ns, int pstride, int fstride, int foff, int c,
+                               const float *pts, const float *feats, const float *centers, const int32_t *idx,
+                               const float *w1s, const float *t1, int n2, const float *y2, const float *a2, const float *b2,
+                               const float *dsel, const uint8_t *garg, const float *wimg2_t, double *s1part,
+                               sg4d_stream_t stream) {
+    RowGemmArgs args{};
+    if (!fill_src(args.op.g, rows, n, m, ns, pstride, fstride, foff, c, pts, feats, centers, idx) || c > 4 || !w1s || !t1 ||
+        (n2 != 64 && n2 != 128) || !y2 || !a2 || !b2 || !dsel || !garg || !wimg2_t || !s1part)
+        return SG4D_EINVAL;
+    args.op.g.w1s = w1s, args.op.g.t1 = t1;
+    args.op.A = y2, args.op.lda = n2, args.op.s = a2, args.op.t = b2, args.op.dsel = dsel, args.op.garg = garg;
+    args.op.S = ns, args.op.logS = ilog2(ns), args.op.ldsel = n2, args.op.ncols = n2;
+    args.R = rows, args.wimg = wimg2_t, args.s1part = s1part;
+    return launch_row<64, 2, 3, 256>(args, mlp_grid(rows), (cudaStream_t)stream);
+}
+
+extern "C" int sg4d_sa1_bwd_dw2(long long rows, int n, int m, int ns, int pstride, int fstride, int foff, int c,
+                                const float *pts, const float *feats, const float *centers, const int32_t *idx,
+                                const float *w1s, const float *t1, int n2, const float *y2, const float *a2, const float *b2,
+                                const float *dsel, const uint8_t *garg, float *partial, float *dw2, sg4d_stream_t stream) {
+    WgradArgs args{};
+    if (!fill_src(args.Q.g, rows, n, m, ns, pstride, fstride, foff, c, pts, feats, centers, idx) || c > 4 || !w1s || !t1 ||
+        (n2 != 64 && n2 != 128) || !y2 || !a2 || !b2 || !dsel || !garg || !partial || !dw2)
+        return SG4D_EINVAL;
+    args.Q.g.w1s = w1s, args.Q.g.t1 = t1, args.Q.ncols = 64;
+    args.P.A = y2, args.P.lda = n2, args.P.s = a2, args.P.t = b2, args.P.dsel = dsel, args.P.garg = garg, args.P.S = ns;
+    args.P.logS = ilog2(ns), args.P.ldsel = n2, args.P.ncols = n2;
+    const int grid = mlp_grid(rows);
+    args.R = rows, args.partial = partial;
+    args.d_lbo = 4096, args.d_sbo = 512, args.d_type = 1, args.d_kstep = 1024;
+    const int st = launch_wgrad<64, 2, 4>(args, grid, (cudaStream_t)stream);
+    if (st != SG4D_OK) return st;
+    wgrad_reduce_kernel<<<(n2 * 64 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(grid, n2, 64, 64, partial, dw2, 64);
+    return SG4D_LAUNCH_CHECK();
+}
+
+extern "C" int sg4d_sa1_bwd_finalize(int k, long long rows, const double *s1part, const double *moments, const float *w1,
+                                     int ldw, const float *stats, int batch_stats, float *d_w1, int lddw, float *d_g1,
+                                     float *d_be1, sg4d_stream_t stream) {
+    if (k < 3 || k > 7 || rows <= 0 || !s1part || !moments || !w1 || ldw < k || !stats || !d_w1 || lddw < k || !d_g1 || !d_be1)
+        return SG4D_EINVAL;
+    sa1_bwd_finalize_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(k, mlp_grid(rows), s1part, moments, w1, ldw, stats, batch_stats,
+                                                                 d_w1, lddw, d_g1, d_be1);
+    return SG4D_LAUNCH_CHECK();
+}
+
+// SA2: first layer with the grouped rows [feats(idx) | xyz(idx) - centre | 0] gathered by the producers
+extern "C" int sg4d_linear_fwd_grouped(long long rows, int n, int m, int ns, int pstride, int fstride, int foff, int c,
+                                       const float *pts, const float *feats, const float *centers, const int32_t *idx,
+                                       int nout, const float *wimg, float *y, double *partial, sg4d_stream_t stream) {
+    RowGemmArgs args{};
+    if (!fill_src(args.op.g, rows, n, m, ns, pstride, fstride, foff, c, pts, feats, centers, idx) || c <= 0 || (c & 3) ||
+        (fstride & 3) || (foff & 3) || (reinterpret_cast<uintptr_t>(feats) & 15) || c + 4 > 256 || (nout != 64 && nout != 128) ||
+        !wimg || !y || !partial)
+        return SG4D_EINVAL;
+    args.op.ncols = c + 4;
+    args.R = rows, args.wimg = wimg, args.Y = y, args.ldy = nout, args.ycol0 = 0, args.partial = partial;
+    return launch_row_n<5, 0>(nout, args, mlp_grid(rows), (cudaStream_t)stream);
+}
+
+// SA2: dW1 (mout x (c + 3)) = dY1^T x with x gathered on the fly; columns in the grouped order [feats | xyz]
+extern "C" int sg4d_inner_bwd_dw_grouped(long long rows, int n, int m, int ns, int pstride, int fstride, int foff, int c,
+                                         const float *pts, const float *feats, const float *centers, const int32_t *idx,
+                                         int mout, const float *y1, const float *dz1, const float *p1, const float *q1,
+                                         const float *u1, float *partial, float *dw, int lddw, sg4d_stream_t stream) {
+    WgradArgs args{};
+    const int k = c + 3;
+    if (!fill_src(args.Q.g, rows, n, m, ns, pstride, fstride, foff, c, pts, feats, centers, idx) || c <= 0 || (c & 3) ||
+        (fstride & 3) || (foff & 3) || (reinterpret_cast<uintptr_t>(feats) & 15) || k > 224 || k <= 128 || (mout != 64 && mout != 128) ||
+        !y1 || !dz1 || !p1 || !q1 || !u1 || !partial || !dw || lddw < k)
+        return SG4D_EINVAL;
+    args.P.A = y1, args.P.lda = mout, args.P.A2 = dz1, args.P.lda2 = mout, args.P.s = q1, args.P.t = u1, args.P.p = p1;
+    args.P.ncols = mout;
+    args.Q.ncols = c + 4;
+    const int grid = mlp_grid(rows);
+    args.R = rows, args.partial = partial;
+    args.d_lbo = 4096, args.d_sbo = 512, args.d_type = 1, args.d_kstep = 1024;
+    const int st = launch_wgrad<224, 3, 5>(args, grid, (cudaStream_t)stream);
+    if (st != SG4D_OK) return st;
+    wgrad_reduce_kernel<<<(mout * k + 255) / 256, 256, 0, (cudaStream_t)stream>>>(grid, mout, k, 224, partial, dw, lddw);
     return SG4D_LAUNCH_CHECK();
 }

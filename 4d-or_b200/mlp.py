@@ -20,6 +20,14 @@ import torch.nn.functional as F
 from . import _lib
 
 
+CAPTURE = None      # tests set this to a list: every fused scale appends its max-pool selection (garg) for pinned-selection checks
+
+
+def _capture(**kw):
+    if CAPTURE is not None:
+        CAPTURE.append(kw)
+
+
 def pack_weight(w2d):
     """(N, K) fp32 -> the pre-split, pre-swizzled shared-memory image sg4d_linear_fwd streams by bulk TMA."""
     w2d = w2d.contiguous()
@@ -101,6 +109,7 @@ class _FusedSharedMLP(torch.autograd.Function):
         y2, part2, gsel, garg = linear_fwd(y1, n1, pack_weight(w2), n2, scale=s1, shift=t1, group=group, gamma=g2)
         s2, t2, m2, i2 = bn_scale_shift(bn2, part2, rows)
         out = torch.relu(torch.addcmul(t2, gsel, s2))
+        _capture(kind="rows", garg=garg, gsel=gsel, y1=y1, y2=y2, s1=s1, t1=t1)
         ctx.save_for_backward(x, y1, y2, gsel, garg, out, w1, w2, s1, t1, m1, i1, s2, m2, i2)
         ctx.meta = (group, dx_cols, bn1.training or not bn1.track_running_stats,
                     bn2.training or not bn2.track_running_stats)
@@ -175,6 +184,230 @@ class _FusedSharedMLP(torch.autograd.Function):
                           u1.data_ptr(), wt.data_ptr(), d_x.data_ptr(), kp, col)
                 col += n
         return (d_x, d_w1, d_g1, d_be1, d_w2, d_g2, d_be2, None, None, None, None)
+
+
+def _src_args(pts, feats, foff, c, centers, idx):
+    """The grouped-row source arguments shared by section 4 of include/sg4d.h."""
+    b, n, ps = pts.shape
+    m, ns = idx.shape[1], idx.shape[2]
+    f = pts if feats is None else feats
+    return (b * m * ns, n, m, ns, ps, f.shape[2], int(foff), int(c), pts.data_ptr(), f.data_ptr(), centers.data_ptr(),
+            idx.data_ptr())
+
+
+def _bn_mode(bn):
+    """(batch statistics?, update running statistics?, momentum) with nn.BatchNorm2d.forward's bookkeeping."""
+    batch = bn.training or not bn.track_running_stats
+    track = bn.training and bn.track_running_stats
+    momentum = 0.0 if bn.momentum is None else bn.momentum
+    if track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if bn.momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    return batch, track, momentum
+
+
+def _pool_bwd_consts(d_out, out, gsel, s2, m2, i2, rows, batch2, ref):
+    """dsel and the BatchNorm2-backward constants a2, b2 (+ d_gamma2, d_beta2) of a pooled layer."""
+    groups, n2 = out.shape
+    dev = out.device
+    if d_out.stride(1) != 1 or (d_out.stride(0) & 3) or (d_out.data_ptr() & 15):
+        d_out = d_out.contiguous()
+    nparts = _lib.load().sg4d_pool_bwd_prologue_parts() * n2
+    part2 = torch.empty(nparts * 2, dtype=torch.float64, device=dev)
+    dsel = torch.empty(groups, n2, dtype=torch.float32, device=dev)
+    _lib.call("sg4d_pool_bwd_prologue", ref, groups, n2, d_out.stride(0), d_out.data_ptr(), out.data_ptr(), gsel.data_ptr(),
+              s2.data_ptr(), m2.data_ptr(), i2.data_ptr(), dsel.data_ptr(), part2.data_ptr())
+    sums2 = torch.empty(2, n2, dtype=torch.float32, device=dev)
+    _lib.call("sg4d_partial_sums", ref, n2, nparts, part2.data_ptr(), sums2.data_ptr())
+    d_be2, d_g2 = sums2[0], sums2[1]
+    if batch2:
+        a2 = s2 * d_g2 * i2 * (1.0 / rows)
+        b2 = s2 * d_be2 * (1.0 / rows) - a2 * m2
+    else:
+        a2 = torch.zeros_like(s2)
+        b2 = torch.zeros_like(s2)
+    return dsel, a2, b2, d_g2, d_be2
+
+
+class _FusedSA1(torch.autograd.Function):
+    """One scale of the first set-abstraction level, ball-query indices -> pooled features, without the grouped
+    tensor and without y1 (csrc/mlp.cu, "Fused set-abstraction scales"): replaces QueryAndGroup + the shared MLP +
+    max_pool2d (OPS/pointnet2_utils.py:300-337, OPS/pointnet2_modules.py:61-70) for K = 3 + c <= 7 inputs and no
+    gradient into the points.  w1 (64, 3 + c) in the reference's column order [xyz | feats]."""
+
+    @staticmethod
+    def forward(ctx, pts, feats, centers, idx, w1, g1, be1, w2, g2, be2, foff, c, bn1, bn2):
+        src = _src_args(pts, feats, foff, c, centers, idx)
+        rows, dev, k = src[0], pts.device, 3 + c
+        n2 = w2.shape[0]
+        lib = _lib.load()
+        w1 = w1.contiguous()
+        nparts = lib.sg4d_sa_moments_parts()
+        part = torch.empty(nparts * 36, dtype=torch.float64, device=dev)
+        _lib.call("sg4d_sa_moments", pts, *src, part.data_ptr())
+        moments = torch.empty(64, dtype=torch.float64, device=dev)
+        stats1 = torch.empty(4, 64, dtype=torch.float32, device=dev)
+        w1s = torch.empty(8, 64, dtype=torch.float32, device=dev)
+        batch1, track1, mom1 = _bn_mode(bn1)
+        _lib.call("sg4d_sa1_bn1", pts, k, nparts, part.data_ptr(), w1.data_ptr(), k, g1.data_ptr(), be1.data_ptr(), float(bn1.eps),
+                  float(mom1), _lib.ptr(bn1.running_mean if (track1 or not batch1) else None),
+                  _lib.ptr(bn1.running_var if (track1 or not batch1) else None), 0 if batch1 else 1, moments.data_ptr(),
+                  stats1.data_ptr(), w1s.data_ptr())
+        y2 = torch.empty(rows, n2, dtype=torch.float32, device=dev)
+        part2 = torch.empty(lib.sg4d_mlp_partial_doubles(rows), dtype=torch.float64, device=dev)
+        ns = idx.shape[2]
+        gsel = torch.empty(rows // ns, n2, dtype=torch.float32, device=dev)
+        garg = torch.empty(rows // ns, n2, dtype=torch.uint8, device=dev)
+        _lib.call("sg4d_sa1_fwd", pts, *src, w1s.data_ptr(), stats1[1].data_ptr(), n2, pack_weight(w2).data_ptr(), y2.data_ptr(),
+                  part2.data_ptr(), g2.data_ptr(), gsel.data_ptr(), garg.data_ptr())
+        s2, t2, m2, i2 = bn_scale_shift(bn2, part2, rows)
+        out = torch.relu(torch.addcmul(t2, gsel, s2))
+        _capture(kind="sa1", garg=garg, gsel=gsel, y2=y2, stats1=stats1, moments=moments, w1s=w1s)
+        ctx.save_for_backward(pts, feats, centers, idx, y2, gsel, garg, out, w1, w2, stats1, w1s, moments, s2, m2, i2)
+        ctx.meta = (foff, c, batch1, bn2.training or not bn2.track_running_stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        pts, feats, centers, idx, y2, gsel, garg, out, w1, w2, stats1, w1s, moments, s2, m2, i2 = ctx.saved_tensors
+        foff, c, batch1, batch2 = ctx.meta
+        src = _src_args(pts, feats, foff, c, centers, idx)
+        rows, dev, k = src[0], pts.device, 3 + c
+        n2 = w2.shape[0]
+        lib = _lib.load()
+        dsel, a2, b2, d_g2, d_be2 = _pool_bwd_consts(d_out, out, gsel, s2, m2, i2, rows, batch2, pts)
+        t1 = stats1[1]
+        s1part = torch.empty(lib.sg4d_sa1_s1part_doubles(rows), dtype=torch.float64, device=dev)
+        _lib.call("sg4d_sa1_bwd_da", pts, *src, w1s.data_ptr(), t1.data_ptr(), n2, y2.data_ptr(), a2.data_ptr(), b2.data_ptr(),
+                  dsel.data_ptr(), garg.data_ptr(), pack_weight(w2.t()).data_ptr(), s1part.data_ptr())
+        d_w2 = torch.empty(n2, 64, dtype=torch.float32, device=dev)
+        _lib.call("sg4d_sa1_bwd_dw2", pts, *src, w1s.data_ptr(), t1.data_ptr(), n2, y2.data_ptr(), a2.data_ptr(), b2.data_ptr(),
+                  dsel.data_ptr(), garg.data_ptr(), _wgrad_partial(rows, 64, dev).data_ptr(), d_w2.data_ptr())
+        d_w1 = torch.empty(64, k, dtype=torch.float32, device=dev)
+        d_gb1 = torch.empty(2, 64, dtype=torch.float32, device=dev)
+        _lib.call("sg4d_sa1_bwd_finalize", pts, k, rows, s1part.data_ptr(), moments.data_ptr(), w1.data_ptr(), k,
+                  stats1.data_ptr(), 1 if batch1 else 0, d_w1.data_ptr(), k, d_gb1[0].data_ptr(), d_gb1[1].data_ptr())
+        return (None, None, None, None, d_w1, d_gb1[0], d_gb1[1], d_w2, d_g2, d_be2, None, None, None, None)
+
+
+class _FusedSA2(torch.autograd.Function):
+    """One scale of a set-abstraction level whose input features carry a gradient (c % 4 == 0 channels): the grouped
+    rows [feats(idx) | xyz(idx) - centre | 0] are gathered by the operand stagers of the first layer and of its
+    weight-gradient kernel instead of being written to and read back from HBM.  w1 (n1, 3 + c), reference column order."""
+
+    @staticmethod
+    def forward(ctx, pts, feats, centers, idx, cnt, w1, g1, be1, w2, g2, be2, foff, c, bn1, bn2):
+        src = _src_args(pts, feats, foff, c, centers, idx)
+        rows, dev = src[0], pts.device
+        n1, n2, ns = w1.shape[0], w2.shape[0], idx.shape[2]
+        lib = _lib.load()
+        w1g = F.pad(torch.cat([w1[:, 3:], w1[:, :3]], dim=1), (0, 1))        # grouped column order [feats | xyz | 0]
+        y1 = torch.empty(rows, n1, dtype=torch.float32, device=dev)
+        part1 = torch.empty(lib.sg4d_mlp_partial_doubles(rows), dtype=torch.float64, device=dev)
+        _lib.call("sg4d_linear_fwd_grouped", pts, *src, n1, pack_weight(w1g).data_ptr(), y1.data_ptr(), part1.data_ptr())
+        s1, t1, m1, i1 = bn_scale_shift(bn1, part1, rows)
+        y2, part2, gsel, garg = linear_fwd(y1, n1, pack_weight(w2), n2, scale=s1, shift=t1, group=ns, gamma=g2)
+        s2, t2, m2, i2 = bn_scale_shift(bn2, part2, rows)
+        out = torch.relu(torch.addcmul(t2, gsel, s2))
+        _capture(kind="sa2", garg=garg, gsel=gsel, y1=y1, y2=y2, s1=s1, t1=t1)
+        ctx.save_for_backward(pts, feats, centers, idx, cnt, y1, y2, gsel, garg, out, w1g, w2, s1, t1, m1, i1, s2, m2, i2)
+        ctx.meta = (foff, c, bn1.training or not bn1.track_running_stats, bn2.training or not bn2.track_running_stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        pts, feats, centers, idx, cnt, y1, y2, gsel, garg, out, w1g, w2, s1, t1, m1, i1, s2, m2, i2 = ctx.saved_tensors
+        foff, c, batch1, batch2 = ctx.meta
+        src = _src_args(pts, feats, foff, c, centers, idx)
+        rows, dev = src[0], pts.device
+        n1, n2, ns = w1g.shape[0], w2.shape[0], idx.shape[2]
+        b, n = pts.shape[0], pts.shape[1]
+        m = idx.shape[1]
+        kp = c + 4
+        dsel, a2, b2, d_g2, d_be2 = _pool_bwd_consts(d_out, out, gsel, s2, m2, i2, rows, batch2, pts)
+        em1 = (-m1 * i1).contiguous()
+        dz1 = torch.empty(rows, n1, dtype=torch.float32, device=dev)
+        part = torch.empty(_lib.load().sg4d_mlp_partial_doubles(rows), dtype=torch.float64, device=dev)
+        _lib.call("sg4d_pool_bwd_da", pts, rows, n2, n1, ns, y2.data_ptr(), a2.data_ptr(), b2.data_ptr(), dsel.data_ptr(),
+                  garg.data_ptr(), pack_weight(w2.t()).data_ptr(), y1.data_ptr(), s1.data_ptr(), t1.data_ptr(),
+                  i1.data_ptr(), em1.data_ptr(), dz1.data_ptr(), part.data_ptr())
+        sums = torch.empty(2, n1, dtype=torch.float32, device=dev)
+        _lib.call("sg4d_partial_sums", pts, n1, part.numel() // 2, part.data_ptr(), sums.data_ptr())
+        d_be1, d_g1 = sums[0], sums[1]
+        d_w2 = torch.empty(n2, n1, dtype=torch.float32, device=dev)
+        _lib.call("sg4d_pool_bwd_dw", pts, rows, n2, n1, ns, y2.data_ptr(), a2.data_ptr(), b2.data_ptr(), dsel.data_ptr(),
+                  garg.data_ptr(), y1.data_ptr(), s1.data_ptr(), t1.data_ptr(), _wgrad_partial(rows, n1, dev).data_ptr(),
+                  d_w2.data_ptr())
+        p1 = s1.contiguous()
+        if batch1:
+            q1 = s1 * d_g1 * i1 * (1.0 / rows)
+            u1 = s1 * d_be1 * (1.0 / rows) - q1 * m1
+        else:
+            q1 = torch.zeros_like(s1)
+            u1 = torch.zeros_like(s1)
+        d_w1g = torch.empty(n1, c + 3, dtype=torch.float32, device=dev)
+        _lib.call("sg4d_inner_bwd_dw_grouped", pts, *src, n1, y1.data_ptr(), dz1.data_ptr(), p1.data_ptr(), q1.data_ptr(),
+                  u1.data_ptr(), _wgrad_partial(rows, 224, dev).data_ptr(), d_w1g.data_ptr(), c + 3)
+        d_w1 = torch.cat([d_w1g[:, c:], d_w1g[:, :c]], dim=1)               # back to the reference order [xyz | feats]
+        d_feats = None
+        if ctx.needs_input_grad[1]:
+            # dX for the gathered feature columns, then the deterministic scatter back to the source points
+            d_x = torch.empty(rows, kp, dtype=torch.float32, device=dev)
+            col = 0
+            while col < c:
+                nn_ = 128 if c - col >= 128 else 64
+                wt = pack_weight(w1g[:, col:col + nn_].t())
+                _lib.call("sg4d_inner_bwd_dx", pts, rows, n1, nn_, y1.data_ptr(), dz1.data_ptr(), p1.data_ptr(), q1.data_ptr(),
+                          u1.data_ptr(), wt.data_ptr(), d_x.data_ptr(), kp, col)
+                col += nn_
+            d_feats = torch.empty(b, n, c, dtype=torch.float32, device=dev)
+            _lib.call("sg4d_group_rows_grad", pts, b, n, m, ns, c, kp, 0, 0, d_x.data_ptr(), idx.data_ptr(), cnt.data_ptr(),
+                      d_feats.data_ptr())
+        return (None, d_feats, None, None, None, d_w1, d_g1, d_be1, d_w2, d_g2, d_be2, None, None, None, None)
+
+
+def _two_layer(mlp):
+    if len(mlp) != 6:
+        return None
+    c1, b1, r1, c2, b2, r2 = mlp
+    if not (isinstance(c1, nn.Conv2d) and isinstance(b1, nn.BatchNorm2d) and isinstance(c2, nn.Conv2d)
+            and isinstance(b2, nn.BatchNorm2d) and isinstance(r1, nn.ReLU) and isinstance(r2, nn.ReLU)):
+        return None
+    if c1.bias is not None or c2.bias is not None or not b1.affine or not b2.affine:
+        return None
+    return c1, b1, c2, b2
+
+
+def sa_scale_kind(mlp, c, ns, feats_need_grad, feat_stride, foff):
+    """Which fused kernel family evaluates this scale: 'sa1', 'sa2' or None (-> materialised grouped rows)."""
+    layers = _two_layer(mlp)
+    if layers is None or ns not in (8, 16, 32, 64, 128):
+        return None
+    c1, b1, c2, b2 = layers
+    n1, n2 = c1.out_channels, c2.out_channels
+    if n2 not in (64, 128) or (n2 == 64 and ns > 64):
+        return None
+    if not feats_need_grad and c <= 4 and n1 == 64:
+        return "sa1"
+    if n1 in (64, 128) and c % 64 == 0 and 128 < c + 3 <= 224 and feat_stride % 4 == 0 and foff % 4 == 0:
+        return "sa2"
+    return None
+
+
+def fused_sa_scale(kind, pts, feats, foff, c, centers, idx, cnt, mlp):
+    """pts (B,n,S), feats (B,n,Sf) or None, centers (B,m,3), idx (B,m,ns) -> pooled (B*m, C_out)."""
+    c1, b1, c2, b2 = _two_layer(mlp)
+    w1 = c1.weight.view(c1.out_channels, 3 + c)
+    w2 = c2.weight.view(c2.out_channels, c2.in_channels)
+    if kind == "sa1":
+        return _FusedSA1.apply(pts, feats, centers, idx, w1, b1.weight, b1.bias, w2, b2.weight, b2.bias, int(foff), int(c), b1, b2)
+    if kind == "sa2":
+        if feats.data_ptr() % 16:
+            raise RuntimeError("fused SA scale: the feature tensor must be 16-byte aligned")
+        return _FusedSA2.apply(pts, feats, centers, idx, cnt, w1, b1.weight, b1.bias, w2, b2.weight, b2.bias, int(foff), int(c),
+                               b1, b2)
+    raise ValueError(kind)
 
 
 def fused_shared_mlp(x, k0, group, mlp, xyz_last=False):

@@ -101,11 +101,18 @@ class _PointnetSAModuleBase(nn.Module):
         if index is not None and max(nsamples) > 64:
             index = None
         idx, cnt = rows.ball_query_rows(new_xyz, pts, radii, nsamples, index)
+        needs_dx = feats is not None and feats.requires_grad and torch.is_grad_enabled()
         for s, mlp in enumerate(self.mlps):
             assert self.groupers[s].use_xyz, "the hot path always groups xyz (use_xyz=True)"
             k = 3 + c
+            fsrc = feats if feats is not None else pts
+            kind = fused.sa_scale_kind(mlp, c, nsamples[s], needs_dx, fsrc.shape[2], feat_offset)
+            if kind is not None:
+                # ball-query indices -> pooled features in the tensor-core kernels; the grouped tensor never exists
+                outs.append(fused.fused_sa_scale(kind, pts, feats, feat_offset, c, new_xyz, idx[s], cnt[s], mlp)
+                            .view(b, self.npoint, -1))
+                continue
             stride = 8 if k <= 8 else _pad4(k)
-            needs_dx = feats is not None and feats.requires_grad and torch.is_grad_enabled()
             use_fused = fused.supported(mlp, stride, nsamples[s]) and (not needs_dx or c % 64 == 0)
             # feature-first column order when a gradient flows back into the gathered features (aligned dX)
             xyz_last = use_fused and needs_dx

@@ -269,6 +269,69 @@ long long sg4d_wgrad_partial_floats(long long rows, int npad);
 /* out[0:n] = sum of the first, out[n:2n] = sum of the second component of the fp64 partial pairs */
 int sg4d_partial_sums(int n, int nparts, const double *partial, float *out, sg4d_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Section 4 -- fused set-abstraction scales: ball-query indices -> shared MLP, the grouped tensor
+ * (QueryAndGroup's output, OPS/pointnet2_utils.py:300-337) is never materialised.
+ *
+ * Grouped-row source ("SRC" below), common to every entry point of this section:
+ *   rows = b * m * ns grouped rows; row r = (cloud * m + centre) * ns + slot; neighbour i = idx[r]
+ *   pts (b, n, pstride): xyz in columns 0..2;  feats (b, n, fstride): the c feature channels are columns
+ *   foff..foff+c-1 (feats may be pts itself, or NULL when c == 0);  centers (b, m, 3);  ns a power of two.
+ * The grouped row is x = [xyz(i) - centre | feats(i)] for SA1 (the reference's channel order,
+ * utils.py:326-328) and [feats(i) | xyz(i) - centre | 0-pad] for the *_grouped entry points (feature columns
+ * 16-byte aligned; the caller permutes the first layer's weight columns accordingly).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* SA1 (k = 3 + c <= 7): per-CTA partials (sg4d_sa_moments_parts() x 36 doubles, upper triangle) of
+ * M = sum over rows of [x | 1][x | 1]^T.  The first layer is linear in x, so BatchNorm1's batch statistics are a
+ * function of M: replaces the statistics pass of nn.BatchNorm2d over the (B, 64, npoint, nsample) tensor. */
+int sg4d_sa_moments_parts(void);
+int sg4d_sa_moments(long long rows, int n, int m, int ns, int pstride, int fstride, int foff, int c, const float *pts,
+                    const float *feats, const float *centers, const int32_t *idx, double *part, sg4d_stream_t stream);
+/* w1 (64, k) row stride ldw.  Folds the partials into moments (8 x 8 fp64, kept for the backward pass) and emits
+ * stats (4, 64) = BatchNorm1 scale, shift, mean, invstd (batch statistics; running_* updated like nn.BatchNorm2d
+ * in training mode, or USED instead when use_running != 0) and w1s (8, 64) = scale .* W1, input-major, zero rows >= k. */
+int sg4d_sa1_bn1(int k, int nparts, const double *part, const float *w1, int ldw, const float *gamma, const float *beta,
+                 float eps, float momentum, float *running_mean, float *running_var, int use_running, double *moments,
+                 float *stats, float *w1s, sg4d_stream_t stream);
+/* y2 (rows, n2) = relu(W1s x + t1) * W2^T with the first layer recomputed from the gathered neighbour in the operand
+ * stagers (8 FMAs per activation; y1 never exists).  t1 = stats + 64.  n2 in {64, 128}; wimg2 = sg4d_pack_weight of
+ * W2 (n2, 64); partial / gamma2 / gsel / garg exactly as sg4d_linear_fwd with group = ns (8 <= ns <= 64, 128 for n2 = 128). */
+int sg4d_sa1_fwd(long long rows, int n, int m, int ns, int pstride, int fstride, int foff, int c, const float *pts,
+                 const float *feats, const float *centers, const int32_t *idx, const float *w1s, const float *t1, int n2,
+                 const float *wimg2, float *y2, double *partial, const float *gamma2, float *gsel, uint8_t *garg,
+                 sg4d_stream_t stream);
+/* Single-pass backward of the first layer: dz1 = ((dY2) * W2) .* [W1s x + t1 > 0] (dY2 as in sg4d_pool_bwd_da) is
+ * consumed where it is produced; s1part (sg4d_sa1_s1part_doubles(rows)) receives per-CTA partials of
+ * S1 = dz1^T [x | 1] (64 x 8).  wimg2_t = packed image of W2^T (64, n2). */
+long long sg4d_sa1_s1part_doubles(long long rows);
+int sg4d_sa1_bwd_da(long long rows, int n, int m, int ns, int pstride, int fstride, int foff, int c, const float *pts,
+                    const float *feats, const float *centers, const int32_t *idx, const float *w1s, const float *t1,
+                    int n2, const float *y2, const float *a2, const float *b2, const float *dsel, const uint8_t *garg,
+                    const float *wimg2_t, double *s1part, sg4d_stream_t stream);
+/* dW2 (n2 x 64) = dY2^T * relu(W1s x + t1), second operand recomputed; partial: sg4d_wgrad_partial_floats(rows, 64) */
+int sg4d_sa1_bwd_dw2(long long rows, int n, int m, int ns, int pstride, int fstride, int foff, int c, const float *pts,
+                     const float *feats, const float *centers, const int32_t *idx, const float *w1s, const float *t1,
+                     int n2, const float *y2, const float *a2, const float *b2, const float *dsel, const uint8_t *garg,
+                     float *partial, float *dw2, sg4d_stream_t stream);
+/* d_beta1 = S1[:, 7];  d_gamma1 = i1 .* (sum_j W1 .* S1 - m1 .* d_beta1);  dW1 (64 x k, row stride lddw) =
+ * p1 .* S1 - q1 .* (W1 M) - u1 (x) M[:, 7]  (BatchNorm backward, linear in S1 and M; q1 = u1 = 0 unless batch_stats) */
+int sg4d_sa1_bwd_finalize(int k, long long rows, const double *s1part, const double *moments, const float *w1, int ldw,
+                          const float *stats, int batch_stats, float *d_w1, int lddw, float *d_g1, float *d_be1,
+                          sg4d_stream_t stream);
+
+/* SA2-style first layer (c % 4 == 0, c + 4 <= 256): y (rows, nout) = x * W^T with x gathered by the operand stagers;
+ * wimg = sg4d_pack_weight of the (nout, c + 4) weight in grouped column order; partial as sg4d_linear_fwd. */
+int sg4d_linear_fwd_grouped(long long rows, int n, int m, int ns, int pstride, int fstride, int foff, int c,
+                            const float *pts, const float *feats, const float *centers, const int32_t *idx, int nout,
+                            const float *wimg, float *y, double *partial, sg4d_stream_t stream);
+/* dW1 (mout x (c + 3), row stride lddw, grouped column order) = dY1^T * x, dY1 as in sg4d_inner_bwd_dx;
+ * 128 < c + 3 <= 224;  partial: sg4d_wgrad_partial_floats(rows, 224) */
+int sg4d_inner_bwd_dw_grouped(long long rows, int n, int m, int ns, int pstride, int fstride, int foff, int c,
+                              const float *pts, const float *feats, const float *centers, const int32_t *idx, int mout,
+                              const float *y1, const float *dz1, const float *p1, const float *q1, const float *u1,
+                              float *partial, float *dw, int lddw, sg4d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
