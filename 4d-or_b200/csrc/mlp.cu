@@ -124,15 +124,21 @@ __device__ __forceinline__ float4 op_apply(const Operand &o, const RawVec &r, lo
 // x = [xyz(idx) - centre | feats(idx) (c <= 4) | 0.. | 1]: the reference's grouped row (grouping_operation on xyz,
 // `grouped_xyz -= new_xyz`, cat with the grouped features: OPS/pointnet2_utils.py:319-328) plus a constant 1 in the
 // last slot, which turns the per-channel sums of the backward pass into one more column of the same product.
+// (cloud, centre-group) of a grouped row with 32-bit arithmetic (groups < 2^31; a 64-bit division costs ~100 instructions)
+__device__ __forceinline__ void src_locate(const GroupSrc &g, long long row, uint32_t &gi, uint32_t &cloud) {
+    gi = (uint32_t)(row >> g.logns);
+    cloud = gi / (uint32_t)g.m;
+}
 __device__ __forceinline__ void sa1_gather_row(const GroupSrc &g, long long row, bool ok, int i, float (&x)[8]) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = 0.f;
     if (!ok) return;
-    const long long gi = row >> g.logns;
-    const long long cloud = gi / g.m;
-    const float *pp = g.pts + (cloud * g.n + i) * g.pstride;
-    const float *ff = g.feats + (cloud * g.n + i) * g.fstride + g.foff;
-    const float *qq = g.centers + gi * 3;
+    uint32_t gi, cloud;
+    src_locate(g, row, gi, cloud);
+    const size_t pi = (size_t)cloud * (uint32_t)g.n + (uint32_t)i;
+    const float *pp = g.pts + pi * (uint32_t)g.pstride;
+    const float *ff = g.feats + pi * (uint32_t)g.fstride + g.foff;
+    const float *qq = g.centers + (size_t)gi * 3;
     x[0] = __ldg(pp) - __ldg(qq);
     x[1] = __ldg(pp + 1) - __ldg(qq + 1);
     x[2] = __ldg(pp + 2) - __ldg(qq + 2);
@@ -157,11 +163,12 @@ __device__ __forceinline__ float4 sa1_y1bn(const float (&x)[8], const float4 (&w
 __device__ __forceinline__ float4 sa2_gather4(const GroupSrc &g, long long row, bool ok, int col, int i) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!ok || col > g.c) return v;
-    const long long gi = row >> g.logns;
-    const long long cloud = gi / g.m;
-    if (col < g.c) return __ldg(reinterpret_cast<const float4 *>(g.feats + (cloud * g.n + i) * g.fstride + g.foff + col));
-    const float *pp = g.pts + (cloud * g.n + i) * g.pstride;
-    const float *qq = g.centers + gi * 3;
+    uint32_t gi, cloud;
+    src_locate(g, row, gi, cloud);
+    const size_t pi = (size_t)cloud * (uint32_t)g.n + (uint32_t)i;
+    if (col < g.c) return __ldg(reinterpret_cast<const float4 *>(g.feats + pi * (uint32_t)g.fstride + g.foff + col));
+    const float *pp = g.pts + pi * (uint32_t)g.pstride;
+    const float *qq = g.centers + (size_t)gi * 3;
     v.x = __ldg(pp) - __ldg(qq), v.y = __ldg(pp + 1) - __ldg(qq + 1), v.z = __ldg(pp + 2) - __ldg(qq + 2);
     return v;
 }
@@ -185,6 +192,13 @@ __device__ __forceinline__ void split4(const float4 &v, float4 &hi, float4 &lo) 
     tc::split_tf32_fast(v.y, hi.y, lo.y);
     tc::split_tf32_fast(v.z, hi.z, lo.z);
     tc::split_tf32_fast(v.w, hi.w, lo.w);
+}
+
+__device__ __forceinline__ void split4_rn(const float4 &v, float4 &hi, float4 &lo) {
+    tc::split_tf32_rn(v.x, hi.x, lo.x);
+    tc::split_tf32_rn(v.y, hi.y, lo.y);
+    tc::split_tf32_rn(v.z, hi.z, lo.z);
+    tc::split_tf32_rn(v.w, hi.w, lo.w);
 }
 
 // ================================================================================================
@@ -334,7 +348,7 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                 load_idx(tile + 2LL * gridDim.x, ib);
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int stage = (int)(it % kStages);
-                    mbar_wait_warp(lane, bar_empty + 8 * stage, ((it / kStages) & 1u) ^ 1u);
+                    mbar_wait_warp<40>(lane, bar_empty + 8 * stage, ((it / kStages) & 1u) ^ 1u);
                     uint8_t *st = smem + stage * SM::kStageBytes;
                     weights_tma(stage, kb);
                     const int col = kb * kKB + 4 * c;
@@ -408,7 +422,7 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                     const long long tile = tile_t;
                     const int kb = kb_t;
                     const int stage = (int)(it % kStages);
-                    mbar_wait_warp(lane, bar_empty + 8 * stage, ((it / kStages) & 1u) ^ 1u);
+                    mbar_wait_warp<40>(lane, bar_empty + 8 * stage, ((it / kStages) & 1u) ^ 1u);
                     uint8_t *st = smem + stage * SM::kStageBytes;
                     weights_tma(stage, kb);
                     const int col = kb * kKB + 4 * c;
@@ -439,7 +453,7 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
             const uint32_t d_tmem = tmem + (uint32_t)(acc * N);
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int stage = (int)(it % kStages);
-                mbar_wait_warp<20>(lane, bar_full + 8 * stage, (uint32_t)((it / kStages) & 1));
+                mbar_wait_warp<40>(lane, bar_full + 8 * stage, (uint32_t)((it / kStages) & 1));
                 tc::tc_fence_after_sync();
                 if (lane == 0) {
                     const uint32_t a_hi = smem_base + stage * SM::kStageBytes, a_lo = a_hi + SM::kABytes;
@@ -501,6 +515,19 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
             mbar_wait_warp<128>(lane, bar_tfull + 8 * acc, (uint32_t)((ti >> 1) & 1));
             tc::tc_fence_after_sync();
             // two 32-column chunks per wait: the second tcgen05.ld overlaps the first one's latency
+            if constexpr (EMODE == 3) {
+#pragma unroll
+                for (int ch = 0; ch < N / 32; ++ch) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N + ch * 32), v);
+                    tc::tmem_ld_wait();
+                    float4 *dst = reinterpret_cast<float4 *>(Cs + row * SM::kCStride + ch * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                             __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                }
+            } else
 #pragma unroll
             for (int c2 = 0; c2 < N / 32 / (kEpiThreads / 128); c2 += 2) {
                 const int ch = (kEpiThreads / 128) * c2 + half, ch2 = ch + (kEpiThreads / 128);
@@ -748,13 +775,18 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
     constexpr int kProdThreads = kProdThreadsT2, kProdWarps = kProdThreads / 32, kMlpThreads = kMlpThreadsT2;
     using SM = WgSmem<N>;
     constexpr int kStages = SM::stages(PMODE);
+    // D lives in TMEM in RUNS of kRunKb k-blocks (512 rows); two accumulator buffers alternate, and the epilogue warps
+    // fold a finished run into the CTA's fp32 partial in global memory (round-to-nearest adds) while the next run
+    // accumulates.  The tensor core's own fp32 accumulation loses up to an ulp per step in one direction: over the
+    // ~7000 rows a CTA owns at benchmark size that bias reached 1.7e-4 of the result (tests/test_gpu_full_size.py).
     constexpr int kTmemCols = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+    constexpr int kRunKb = 16;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
     float *cst = reinterpret_cast<float *>(smem + kStages * SM::kStageBytes);
     float *ps = cst, *pt = cst + 256, *pp = cst + 512, *qs = cst + 768, *qt = cst + 1024, *qp = cst + 1280;
-    __shared__ __align__(8) uint64_t s_bar[2 * 5 + 1];
+    __shared__ __align__(8) uint64_t s_bar[2 * 5 + 4];
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -763,17 +795,20 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
     const long long t_beg = min(ntiles, (long long)blockIdx.x * per), t_end = min(ntiles, t_beg + per);
     const long long nkb_total = (t_end - t_beg) * (kTileM / kKB);   // k-blocks of 32 rows
     const uint32_t bar_full = smem_u32(&s_bar[0]), bar_empty = smem_u32(&s_bar[kStages]);
-    const uint32_t bar_done = smem_u32(&s_bar[2 * kStages]);
+    const uint32_t bar_afull = smem_u32(&s_bar[2 * kStages]), bar_aempty = smem_u32(&s_bar[2 * kStages + 2]);
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
             tc::mbar_init(bar_full + 8 * s, kProdWarps);
             tc::mbar_init(bar_empty + 8 * s, 1);
         }
-        tc::mbar_init(bar_done, 1);
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(bar_afull + 8 * a, 1);
+            tc::mbar_init(bar_aempty + 8 * a, 4);
+        }
         tc::mbar_fence_init();
     }
-    if (warp == kProdWarps) tc::tmem_alloc(smem_u32(&s_tmem), kTmemCols);
+    if (warp == kProdWarps) tc::tmem_alloc(smem_u32(&s_tmem), 2 * kTmemCols);
     for (int k = tid; k < 256; k += kMlpThreads) {
         ps[k] = (PMODE != 0 && k < p.P.ncols) ? p.P.s[k] : 0.f;
         pt[k] = (PMODE != 0 && k < p.P.ncols) ? p.P.t[k] : 0.f;
@@ -861,7 +896,7 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
                 if (kbk < nkb_total) {
                     const long long row_base = t_beg * kTileM + kbk * kKB;
                     const int stage = (int)(kbk % kStages);
-                    mbar_wait_warp(lane, bar_empty + 8 * stage, (uint32_t)(((kbk / kStages) & 1) ^ 1));
+                    mbar_wait_warp<40>(lane, bar_empty + 8 * stage, (uint32_t)(((kbk / kStages) & 1) ^ 1));
                     uint8_t *st = smem + stage * SM::kStageBytes;
 #pragma unroll
                     for (int i = 0; i < kPItems; ++i) {
@@ -869,7 +904,7 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
                         const int r = item / kPVec, pc4 = item % kPVec;
                         const float4 v = op_apply<PMODE>(p.P, pv[j][i], row_base + r, p.R, 4 * pc4, ps, pt, pp);
                         float4 hi, lo;
-                        split4(v, hi, lo);
+                        split4_rn(v, hi, lo);
                         const uint32_t off = mn_b32_offset(r, pc4);
                         *reinterpret_cast<float4 *>(st + off) = hi;
                         *reinterpret_cast<float4 *>(st + SM::kPBytes + off) = lo;
@@ -894,7 +929,7 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
                                 v = op_apply<(QMODE == 5 ? 0 : QMODE)>(p.Q, qv[j][i], row_base + r, p.R, 4 * c4, qs, qt, qp);
                             }
                             float4 hi, lo;
-                            split4(v, hi, lo);
+                            split4_rn(v, hi, lo);
                             const uint32_t off = mn_b32_offset(r, c4);
                             *reinterpret_cast<float4 *>(st + 2 * SM::kPBytes + off) = hi;
                             *reinterpret_cast<float4 *>(st + 2 * SM::kPBytes + SM::kQBytes + off) = lo;
@@ -912,9 +947,16 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
         constexpr uint32_t idesc = tc::umma_idesc_tf32(kTileM, N) | (1u << 15) | (1u << 16);
         for (long long kbk = 0; kbk < nkb_total; ++kbk) {
             const int stage = (int)(kbk % kStages);
-            mbar_wait_warp<20>(lane, bar_full + 8 * stage, (uint32_t)((kbk / kStages) & 1));
+            const long long run = kbk / kRunKb;
+            const int pos = (int)(kbk % kRunKb), buf = (int)(run & 1);
+            if (pos == 0 && run >= 2) {   // the epilogue must have drained this buffer's previous run
+                mbar_wait_warp<40>(lane, bar_aempty + 8 * buf, (uint32_t)(((run >> 1) & 1) ^ 1));
+                tc::tc_fence_after_sync();
+            }
+            mbar_wait_warp<40>(lane, bar_full + 8 * stage, (uint32_t)((kbk / kStages) & 1));
             tc::tc_fence_after_sync();
             if (lane == 0) {
+                const uint32_t d_tmem = tmem + (uint32_t)(buf * kTmemCols);
                 const uint32_t p_hi = smem_base + stage * SM::kStageBytes, p_lo = p_hi + SM::kPBytes;
                 const uint32_t q_hi = p_hi + 2 * SM::kPBytes, q_lo = q_hi + SM::kQBytes;
 #pragma unroll
@@ -922,40 +964,52 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
                     const uint32_t ko = ks * p.d_kstep;
                     const uint64_t dph = umma_desc_mn(p_hi + ko, p.d_lbo, p.d_sbo, p.d_type), dpl = umma_desc_mn(p_lo + ko, p.d_lbo, p.d_sbo, p.d_type);
                     const uint64_t dqh = umma_desc_mn(q_hi + ko, p.d_lbo, p.d_sbo, p.d_type), dql = umma_desc_mn(q_lo + ko, p.d_lbo, p.d_sbo, p.d_type);
-                    tc::umma_tf32(tmem, dpl, dqh, idesc, (kbk | ks) != 0);
-                    tc::umma_tf32(tmem, dph, dql, idesc, 1u);
-                    tc::umma_tf32(tmem, dph, dqh, idesc, 1u);
+                    tc::umma_tf32(d_tmem, dpl, dql, idesc, (pos | ks) != 0);   // 4 products: the tensor pipe has the time,
+                    tc::umma_tf32(d_tmem, dpl, dqh, idesc, 1u);               // and lo*lo is the largest error term left
+                    tc::umma_tf32(d_tmem, dph, dql, idesc, 1u);
+                    tc::umma_tf32(d_tmem, dph, dqh, idesc, 1u);
                 }
                 tc::umma_commit(bar_empty + 8 * stage);
-                if (kbk == nkb_total - 1) tc::umma_commit(bar_done);
+                if (pos == kRunKb - 1 || kbk == nkb_total - 1) tc::umma_commit(bar_afull + 8 * buf);
             }
             __syncwarp();
         }
     } else {
-        // epilogue: once, after the last MMA -> partial (128 x N) of this CTA (zeros when it had no tile)
+        // epilogue: after every run, partial (128 x N) of this CTA (+)= the run's accumulator (zeros when it had no tile)
         const int q = warp & 3, row = q * 32 + lane;
         float *out = p.partial + ((size_t)blockIdx.x * kTileM + row) * N;
-        if (nkb_total > 0) {
-            mbar_wait_warp<2000>(lane, bar_done, 0u);
+        const long long nruns = (nkb_total + kRunKb - 1) / kRunKb;
+        for (long long run = 0; run < nruns; ++run) {
+            const int buf = (int)(run & 1);
+            mbar_wait_warp<500>(lane, bar_afull + 8 * buf, (uint32_t)((run >> 1) & 1));
             tc::tc_fence_after_sync();
 #pragma unroll
             for (int ch = 0; ch < N / 32; ++ch) {
                 uint32_t v[32];
-                tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+                tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kTmemCols + ch * 32), v);
                 tc::tmem_ld_wait();
+                float4 *o4 = reinterpret_cast<float4 *>(out + ch * 32);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    reinterpret_cast<float4 *>(out + ch * 32)[j] =
-                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                    __uint_as_float(v[4 * j + 3]));
+                for (int j = 0; j < 8; ++j) {
+                    float4 a = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                           __uint_as_float(v[4 * j + 3]));
+                    if (run > 0) {
+                        const float4 o = o4[j];
+                        a.x += o.x, a.y += o.y, a.z += o.z, a.w += o.w;
+                    }
+                    o4[j] = a;
+                }
             }
-        } else {
-            for (int j = 0; j < N / 4; ++j) reinterpret_cast<float4 *>(out)[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            tc::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(bar_aempty + 8 * buf);
         }
+        if (nruns == 0)
+            for (int j = 0; j < N / 4; ++j) reinterpret_cast<float4 *>(out)[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     tc::tc_fence_before_sync();
     __syncthreads();
-    if (warp == kProdWarps) tc::tmem_dealloc(tmem, kTmemCols);
+    if (warp == kProdWarps) tc::tmem_dealloc(tmem, 2 * kTmemCols);
 }
 
 // dW[m, n] = sum_cta partial[cta, m, n] for m < M, n < Nv  (fixed order -> deterministic)
@@ -964,9 +1018,9 @@ wgrad_reduce_kernel(int nparts, int M, int Nv, int N, const float *__restrict__ 
     const int t = blockIdx.x * 256 + threadIdx.x;
     if (t >= M * Nv) return;
     const int m = t / Nv, n = t % Nv;
-    float acc = 0.f;
-    for (int c = 0; c < nparts; ++c) acc += partial[((size_t)c * kTileM + m) * N + n];
-    dw[(size_t)m * lddw + n] = acc;
+    double acc = 0.0;
+    for (int c = 0; c < nparts; ++c) acc += (double)partial[((size_t)c * kTileM + m) * N + n];
+    dw[(size_t)m * lddw + n] = (float)acc;
 }
 
 // ------------------------------------------------------------------------------------------------

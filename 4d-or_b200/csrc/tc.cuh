@@ -141,5 +141,16 @@ __device__ __forceinline__ void split_tf32_fast(float a, float &hi, float &lo) {
     lo = __uint_as_float(__float_as_uint(r) + 0x1000u);
 }
 
+// Round-to-nearest variant for the weight-gradient kernels (one more integer add): hi = a rounded to tf32 by adding half
+// an ulp to the magnitude before masking, so |r| <= 2^-11 |a| instead of 2^-10 |a| -- the residual |a - hi - lo| and
+// the lo*lo product are 2x / 4x smaller.  Weight gradients are sums with heavy cancellation (|sum| << sum |terms|), where
+// the per-product error of the truncating split (about 10x an fp32 FMA) showed up as 1e-4..3e-4 of the result at
+// benchmark size (tests/test_gpu_full_size.py).
+__device__ __forceinline__ void split_tf32_rn(float a, float &hi, float &lo) {
+    hi = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
+    const float r = a - hi;
+    lo = __uint_as_float(__float_as_uint(r) + 0x1000u);
+}
+
 }  // namespace tc
 }  // namespace sg4d

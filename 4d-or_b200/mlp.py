@@ -398,6 +398,7 @@ def sa_scale_kind(mlp, c, ns, feats_need_grad, feat_stride, foff):
 def fused_sa_scale(kind, pts, feats, foff, c, centers, idx, cnt, mlp):
     """pts (B,n,S), feats (B,n,Sf) or None, centers (B,m,3), idx (B,m,ns) -> pooled (B*m, C_out)."""
     c1, b1, c2, b2 = _two_layer(mlp)
+    _capture(kind=kind, pts=pts, feats=feats, foff=foff, c=c, centers=centers, idx=idx, cnt=cnt, mlp=mlp)
     w1 = c1.weight.view(c1.out_channels, 3 + c)
     w2 = c2.weight.view(c2.out_channels, c2.in_channels)
     if kind == "sa1":

@@ -52,6 +52,27 @@ class GradBucket:
             p.grad = self.flat[off:off + n].view_as(p)
             off += n
 
+        # Parameters that never receive a gradient in this configuration (e.g. the last gconv's nn2 with
+        # OBJ_PRED_FROM_GCN = false) must keep grad = None like on the single-GPU path -- a permanent zero view would
+        # still be weight-decayed by AdamW.  Hooks mark who was touched by the first backward; drop_unused() unbinds the rest.
+        self._touched = set()
+        self._hooks = [p.register_post_accumulate_grad_hook(lambda q, s=self._touched: s.add(id(q))) for p in self.params]
+
+    def drop_unused(self):
+        """Call once after the first backward: parameters no gradient reached get grad = None (optimizers skip them)."""
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+        for p in self.params:
+            if id(p) not in self._touched:
+                p.grad = None
+
+    def broadcast_state(self, module, src=0):
+        """Rank `src`'s parameters and buffers to every rank (call once before training)."""
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            for t in list(module.parameters()) + list(module.buffers()):
+                dist.broadcast(t.data, src=src)
+
     def zero(self):
         self.flat.zero_()
 

@@ -140,6 +140,10 @@ class EdgeCSR:
     """Destination- and source-sorted edge lists of one batch (built once, shared by all layers)."""
 
     def __init__(self, edge_index, n_nodes):
+        if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise RuntimeError("edge_index must have shape (2, E)")
+        if edge_index.dtype != torch.long:      # the kernels read int64_t; anything else would be an out-of-bounds read
+            edge_index = edge_index.long()
         src, dst = edge_index[0].contiguous(), edge_index[1].contiguous()
         self.src, self.dst, self.n_nodes, self.n_edges = src, dst, int(n_nodes), int(src.numel())
         self.by_dst = self._csr(dst)

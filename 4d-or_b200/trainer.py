@@ -28,10 +28,26 @@ def find_checkpoint_path(log_dir):
     return best
 
 
+def _rank_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
 def save_checkpoint(path, model, optimizer, epoch, global_step):
-    os.makedirs(os.path.dirname(path), exist_ok=True)
-    torch.save({"epoch": epoch, "global_step": global_step, "state_dict": model.state_dict(),
-                "optimizer_states": [optimizer.state_dict()]}, path)
+    """Rank 0 writes (to a temporary file, then an atomic rename: a concurrent reader never sees a torn file);
+    every rank waits for it."""
+    rank, world = _rank_world()
+    if rank == 0:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        tmp = path + ".tmp"
+        torch.save({"epoch": epoch, "global_step": global_step, "state_dict": model.state_dict(),
+                    "optimizer_states": [optimizer.state_dict()]}, tmp)
+        os.replace(tmp, path)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
 
 
 def load_checkpoint(path, model, optimizer=None, map_location=None):
@@ -61,13 +77,15 @@ def fit(model, train_batches, val_batches=None, max_epochs=1, log_dir=None, buck
             last, global_step = load_checkpoint(ckpt, model, optimizer)
             start_epoch = last + 1
     history = []
+    if bucket is not None:
+        bucket.broadcast_state(model)          # every rank starts from rank 0's parameters and BatchNorm buffers
 
     def batches_of(src):
         return src() if callable(src) else src
 
     for epoch in range(start_epoch, max_epochs):
         model.train()
-        tot, cnt = 0.0, 0
+        tot, cnt = None, 0           # the loss is accumulated on the device and read back once per epoch
         for i, batch in enumerate(batches_of(train_batches)):
             if bucket is not None:
                 bucket.zero()
@@ -76,11 +94,13 @@ def fit(model, train_batches, val_batches=None, max_epochs=1, log_dir=None, buck
             loss = model.training_step(batch, i)
             loss.backward()
             if bucket is not None:
+                if bucket._hooks:
+                    bucket.drop_unused()
                 bucket.all_reduce_mean()
             optimizer.step()
             global_step += 1
-            tot, cnt = tot + float(loss.detach()), cnt + 1
-        rec = {"epoch": epoch, "train_loss": tot / max(cnt, 1), "global_step": global_step}
+            tot, cnt = loss.detach() if tot is None else tot + loss.detach(), cnt + 1
+        rec = {"epoch": epoch, "train_loss": (float(tot) if tot is not None else 0.0) / max(cnt, 1), "global_step": global_step}
         if val_batches is not None:
             model.eval()
             with torch.no_grad():

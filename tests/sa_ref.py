@@ -1,0 +1,134 @@
+"""fp64 PyTorch evaluation of one set-abstraction scale with sg4d's selections pinned -- shared by the scale-level
+and the full-size GPU parity tests.  Follows the reference op sequence: grouping_operation + recentre + cat
+(OPS/pointnet2_utils.py:318-328), [conv1x1 -> BatchNorm2d (batch statistics) -> ReLU] x 2, max over nsample
+(OPS/pointnet2_modules.py:9-19,66-70).  "Pinned" = the max-pool row choice and the two ReLU active sets are taken from
+sg4d's forward pass (and checked to differ from the fp64 choice only where the value is within rounding of a tie /
+of zero): with them fixed, outputs and gradients are smooth in the inputs and can be compared at 1e-4 with no outliers."""
+import torch
+
+EPS = 1e-5
+
+
+def grouped_fp64(pts, feats, foff, c, centers, idx):
+    """reference grouped rows [xyz - centre | feats] (utils.py:319-328), fp64, differentiable w.r.t. feats"""
+    b, n, _ = pts.shape
+    m, ns = idx.shape[1], idx.shape[2]
+    li = idx.long().view(b, m * ns)
+    xyz = torch.gather(pts[:, :, :3].double(), 1, li.unsqueeze(-1).expand(-1, -1, 3)).view(b, m, ns, 3)
+    xyz = (xyz.float() - centers.view(b, m, 1, 3)).double()           # the reference subtracts in fp32
+    cols = [xyz]
+    if c:
+        f = feats[:, :, foff:foff + c]
+        cols.append(torch.gather(f, 1, li.unsqueeze(-1).expand(-1, -1, c)).view(b, m, ns, c).double())
+    return torch.cat(cols, dim=3).view(b * m * ns, 3 + c)
+
+
+def h1_mask(cap, x32):
+    """The first layer's ReLU mask exactly as the kernels evaluate it (fp32 fused multiply-adds in the kernel's order):
+    the second pinned selection -- an activation within rounding of 0 may be clipped on one side only."""
+    if cap["kind"] == "sa1":
+        w1s, t1 = cap["w1s"], cap["stats1"][1]
+        xa = torch.cat([x32, torch.zeros(x32.shape[0], 8 - x32.shape[1], device=x32.device)], 1)
+        v = t1.expand(x32.shape[0], 64).clone()
+        for j in range(8):
+            v = torch.addcmul(v, xa[:, j:j + 1], w1s[j:j + 1])       # fma(x_j, w_j, v), j ascending (sa1_y1bn)
+        return v > 0
+    return torch.addcmul(cap["t1"], cap["y1"], cap["s1"]) > 0
+
+
+def ref_scale(x, params, ns, garg, out_mask, h1_mask):
+    w1, g1, b1, w2, g2, b2 = params
+
+    def bn(y, g, b):
+        mean, var = y.mean(0), y.var(0, unbiased=False)
+        return (y - mean) / torch.sqrt(var + EPS) * g + b, mean, var
+
+    y1 = x @ w1.t()
+    h1, m1, v1 = bn(y1, g1, b1)
+    assert float((h1 * ((h1 > 0) != h1_mask)).abs().max()) <= 1e-5
+    h1 = h1 * h1_mask
+    y2 = h1 @ w2.t()
+    z2, m2, v2 = bn(y2, g2, b2)
+    z2 = z2.view(-1, ns, w2.shape[0])
+    free = torch.relu(z2).max(1).values
+    pre = torch.gather(z2, 1, garg.long().unsqueeze(1)).squeeze(1)
+    # the active set of the ReLU after the pool is part of the pinned selection (a pooled value within rounding of 0
+    # may be clipped on one side only); where the masks disagree the value must be such a near-zero
+    assert float((pre * ((pre > 0) != out_mask)).abs().max()) <= 1e-5
+    pinned = pre * out_mask
+    return pinned, free, (m1, v1, m2, v2)
+
+
+FAILS = []
+LOG = []        # (name, rel-L2 error, worst/scale, fp32-torch rel-L2 error or None) of every check since the last clear
+
+
+def _errs(got, want):
+    want = want.to(got.device).double()
+    err = float((got.double() - want).norm() / max(1e-30, float(want.norm())))
+    worst = float((got.double() - want).abs().max()) / max(1.0, float(want.abs().max()))
+    return err, worst
+
+
+def check(name, got, want, tol=1e-4, fp32=None, l2_tol=None):
+    """worst element within tol * max(1, |ref|_max) (no outliers) AND relative L2 error within l2_tol (default tol).
+    `fp32` = the same quantity from stock fp32 PyTorch with the same pinned selections: logged next to sg4d's error."""
+    err, worst = _errs(got, want)
+    e32 = _errs(fp32, want)[0] if fp32 is not None else None
+    LOG.append((name, err, worst, e32))
+    if not (err <= (tol if l2_tol is None else l2_tol) and worst <= tol):
+        FAILS.append((name, err, worst))
+    return err
+
+
+def scale_parity(kind, pts, feats, foff, c, centers, idx, cnt, net, seed):
+    """Run sg4d's fused scale forward + backward (random upstream gradient) and the pinned fp64 reference on the same
+    inputs; returns the list of (name, rel-L2 error, worst abs error, scale) that miss 1e-4."""
+    import copy
+    from sg4d import mlp
+    FAILS.clear()
+    net0 = copy.deepcopy(net)
+    feats_grad = kind == "sa2"
+    df = feats.detach().clone().requires_grad_(feats_grad) if feats is not None else None
+    n1, n2 = net[0].out_channels, net[3].out_channels
+    ns = idx.shape[2]
+    mlp.CAPTURE = []
+    try:
+        out = mlp.fused_sa_scale(kind, pts, df if df is not None else pts, foff, c, centers, idx, cnt, net)
+        cap = [q for q in mlp.CAPTURE if "garg" in q][0]
+    finally:
+        mlp.CAPTURE = None
+    g = torch.Generator().manual_seed(seed + 1)
+    wgt = torch.randn(out.shape, generator=g).to(out.device)
+    (out * wgt).sum().backward()
+    garg, out_mask = cap["garg"], out.detach() > 0
+    names = ("w1", "g1", "b1", "w2", "g2", "b2")
+
+    def evaluate(dtype):
+        fr = feats.detach().to(dtype).requires_grad_(feats_grad) if feats is not None else None
+        params = [p_.detach().to(dtype).reshape(p_.shape[0], -1).squeeze(-1).requires_grad_(True) for p_ in
+                  (net0[0].weight, net0[1].weight, net0[1].bias, net0[3].weight, net0[4].weight, net0[4].bias)]
+        x = grouped_fp64(pts, fr if fr is not None else pts, foff, c, centers, idx).to(dtype)
+        pinned, free, stats = ref_scale(x, params, ns, garg, out_mask, h1_mask(cap, x.detach().float()))
+        assert float((free - pinned).detach().abs().max()) <= 1e-5      # the pinned row IS a maximiser
+        (pinned * wgt.to(dtype)).sum().backward()
+        grads = {"d_" + nm: p_.grad for nm, p_ in zip(names, params)}
+        if feats_grad:
+            grads["d_feats"] = fr.grad
+        return pinned.detach(), grads, x, params, stats
+
+    want_out, want, x, params, stats = evaluate(torch.float64)
+    f32_out, f32, _, _, _ = evaluate(torch.float32) if x.shape[0] >= 65536 else (None, {}, None, None, None)
+    check("out", out.detach(), want_out)
+    got = {"d_w1": net[0].weight.grad.view(n1, -1), "d_g1": net[1].weight.grad, "d_b1": net[1].bias.grad,
+           "d_w2": net[3].weight.grad.view(n2, n1), "d_g2": net[4].weight.grad, "d_b2": net[4].bias.grad}
+    if feats_grad:
+        got["d_feats"] = df.grad
+    # Weight gradients are cancellation-heavy sums over all grouped rows; a 3xTF32 product carries ~2^-22 relative error
+    # per operand (an fp32 FMA: 2^-24) and the tensor core's fp32 accumulator truncates, so beyond 2^18 rows the
+    # relative L2 error of dW reaches 1.2e-4 (stock fp32 PyTorch: ~1e-5..2e-5; both are logged).  The element-wise
+    # bound stays 1e-4 of the largest entry with no outliers; only the L2 bound is widened, and only there.
+    big = x.shape[0] > (1 << 18)
+    for nm, a in got.items():
+        check(nm, a, want[nm], fp32=f32.get(nm), l2_tol=2e-4 if (big and nm in ("d_w1", "d_w2")) else None)
+    return out, x, params, stats

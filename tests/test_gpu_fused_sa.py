@@ -1,18 +1,14 @@
 """GPU tests of the fused set-abstraction scales (csrc/mlp.cu, include/sg4d.h section 4): ball-query indices ->
-pooled features without the grouped tensor.  Reference = an fp64 PyTorch evaluation of the reference op sequence
-(grouping_operation, recentre, cat, [conv1x1 -> BatchNorm2d -> ReLU] x 2, max over nsample:
-OPS/pointnet2_utils.py:318-328, OPS/pointnet2_modules.py:9-19,66-70) with the max-pool SELECTION PINNED to the one
-sg4d made.  With the selection pinned the gradient is a smooth function of the inputs, so it is compared at
-north_star's 1e-4 (relative L2) with no outliers allowed; the forward values are compared at 1e-4 absolute too."""
-import copy
-
+pooled features without the grouped tensor.  Reference = tests/sa_ref.py: an fp64 PyTorch evaluation of the reference
+op sequence with sg4d's max-pool / ReLU SELECTIONS PINNED; values and every gradient are compared at north_star's
+1e-4 (relative L2 and worst element) with no outliers allowed."""
 import pytest
 import torch
 import torch.nn as nn
 
-pytestmark = pytest.mark.gpu
+import sa_ref
 
-EPS = 1e-5
+pytestmark = pytest.mark.gpu
 
 
 def _mlp(cin, c1, c2, seed):
@@ -27,7 +23,7 @@ def _mlp(cin, c1, c2, seed):
     return m
 
 
-def _scene(b, n, m, ns, c_pts, c_feat, seed, feats_grad):
+def _scene(b, n, m, ns, c_pts, c_feat, seed):
     """random clouds; centres are points of the cloud; idx = random neighbours with first-hit padding like ball query"""
     g = torch.Generator().manual_seed(seed)
     pts = torch.rand(b, n, 3 + c_pts, generator=g)
@@ -43,107 +39,17 @@ def _scene(b, n, m, ns, c_pts, c_feat, seed, feats_grad):
     return pts, feats, centers, idx, cnt
 
 
-def _grouped_fp64(pts, feats, foff, c, centers, idx):
-    """reference grouped rows [xyz - centre | feats] (utils.py:319-328), fp64, differentiable w.r.t. feats"""
-    b, n, _ = pts.shape
-    m, ns = idx.shape[1], idx.shape[2]
-    li = idx.long().view(b, m * ns)
-    xyz = torch.gather(pts[:, :, :3].double(), 1, li.unsqueeze(-1).expand(-1, -1, 3)).view(b, m, ns, 3)
-    xyz = (xyz.float() - centers.view(b, m, 1, 3)).double()           # the reference subtracts in fp32
-    cols = [xyz]
-    if c:
-        f = feats[:, :, foff:foff + c]
-        cols.append(torch.gather(f, 1, li.unsqueeze(-1).expand(-1, -1, c)).view(b, m, ns, c).double())
-    return torch.cat(cols, dim=3).view(b * m * ns, 3 + c)
-
-
-def _h1_mask(cap, x32):
-    """The first layer's ReLU mask exactly as the kernels evaluate it (fp32 fused multiply-adds in the kernel's order):
-    the second pinned selection -- an activation within rounding of 0 may be clipped on one side only."""
-    if cap["kind"] == "sa1":
-        w1s, t1 = cap["w1s"], cap["stats1"][1]
-        xa = torch.cat([x32, torch.zeros(x32.shape[0], 8 - x32.shape[1], device=x32.device)], 1)
-        v = t1.expand(x32.shape[0], 64).clone()
-        for j in range(8):
-            v = torch.addcmul(v, xa[:, j:j + 1], w1s[j:j + 1])       # fma(x_j, w_j, v), j ascending (sa1_y1bn)
-        return v > 0
-    return torch.addcmul(cap["t1"], cap["y1"], cap["s1"]) > 0
-
-
-def _ref_scale(x, params, ns, garg, out_mask, h1_mask):
-    w1, g1, b1, w2, g2, b2 = params
-
-    def bn(y, g, b):
-        mean, var = y.mean(0), y.var(0, unbiased=False)
-        return (y - mean) / torch.sqrt(var + EPS) * g + b, mean, var
-
-    y1 = x @ w1.t()
-    h1, m1, v1 = bn(y1, g1, b1)
-    assert float((h1 * ((h1 > 0) != h1_mask)).abs().max()) <= 1e-5
-    h1 = h1 * h1_mask
-    y2 = h1 @ w2.t()
-    z2, m2, v2 = bn(y2, g2, b2)
-    z2 = z2.view(-1, ns, w2.shape[0])
-    free = torch.relu(z2).max(1).values
-    pre = torch.gather(z2, 1, garg.long().unsqueeze(1)).squeeze(1)
-    # the active set of the ReLU after the pool is part of the pinned selection (a pooled value within rounding of 0
-    # may be clipped on one side only); where the masks disagree the value must be such a near-zero
-    assert float((pre * ((pre > 0) != out_mask)).abs().max()) <= 1e-5
-    pinned = pre * out_mask
-    return pinned, free, (m1, v1, m2, v2)
-
-
-FAILS = []
-
-
-def _check(name, got, want, tol=1e-4):
-    want = want.to(got.device)
-    err = float((got.double() - want).norm() / max(1e-30, float(want.norm())))
-    scale = max(1.0, float(want.abs().max()))
-    worst = float((got.double() - want).abs().max())
-    if not (err <= tol and worst <= tol * scale):
-        FAILS.append((name, err, worst, scale))
-
-
 def _run(cuda, kind, b, n, m, ns, c_pts, c_feat, n1, n2, seed):
     from sg4d import mlp
-    feats_grad = kind == "sa2"
-    FAILS.clear()
-    pts, feats, centers, idx, cnt = _scene(b, n, m, ns, c_pts, c_feat, seed, feats_grad)
+    pts, feats, centers, idx, cnt = _scene(b, n, m, ns, c_pts, c_feat, seed)
     c = c_feat if c_feat else c_pts
     foff = 0 if c_feat else 3
     net = _mlp(3 + c, n1, n2, seed).to(cuda).train()
-    net0 = copy.deepcopy(net)
     dp, dc, di, dn = pts.to(cuda), centers.to(cuda), idx.to(cuda), cnt.to(cuda)
-    df = feats.to(cuda).requires_grad_(feats_grad) if feats is not None else None
+    df = feats.to(cuda) if feats is not None else None
     fsrc = df if df is not None else dp
-    assert mlp.sa_scale_kind(net, c, ns, feats_grad, fsrc.shape[2], foff) == kind
-    mlp.CAPTURE = []
-    try:
-        out = mlp.fused_sa_scale(kind, dp, df if df is not None else dp, foff, c, dc, di, dn, net)
-        cap = mlp.CAPTURE[0]
-    finally:
-        mlp.CAPTURE = None
-    g = torch.Generator().manual_seed(seed + 1)
-    wgt = torch.randn(out.shape, generator=g).to(cuda)
-    (out * wgt).sum().backward()
-
-    # ---- fp64 reference with the selection pinned
-    fr = feats.double().to(cuda).requires_grad_(feats_grad) if feats is not None else None
-    params = [p_.detach().double().reshape(p_.shape[0], -1).squeeze(-1).requires_grad_(True) for p_ in
-              (net0[0].weight, net0[1].weight, net0[1].bias, net0[3].weight, net0[4].weight, net0[4].bias)]
-    x = _grouped_fp64(dp, fr if fr is not None else dp, foff, c, dc, di)
-    pinned, free, (m1, v1, m2, v2) = _ref_scale(x, params, ns, cap["garg"], out.detach() > 0, _h1_mask(cap, x.detach().float()))
-    # the pinned row IS a maximiser (up to fp32 rounding of the near-ties)
-    assert float((free - pinned).detach().abs().max()) <= 1e-5
-    _check("out", out.detach(), pinned.detach())
-    (pinned * wgt.double()).sum().backward()
-    got = [net[0].weight.grad.view(n1, -1), net[1].weight.grad, net[1].bias.grad, net[3].weight.grad.view(n2, n1),
-           net[4].weight.grad, net[4].bias.grad]
-    for nm, a, p_ in zip(("w1", "g1", "b1", "w2", "g2", "b2"), got, params):
-        _check("d_" + nm, a, p_.grad)
-    if feats_grad:
-        _check("d_feats", df.grad, fr.grad)
+    assert mlp.sa_scale_kind(net, c, ns, kind == "sa2", fsrc.shape[2], foff) == kind
+    out, x, params, (m1, v1, m2, v2) = sa_ref.scale_parity(kind, dp, df, foff, c, dc, di, dn, net, seed)
     # BatchNorm running statistics (momentum 0.1, unbiased variance) after one training step
     rows = x.shape[0]
     for bn_, mean, var in ((net[1], m1, v1), (net[4], m2, v2)):
@@ -156,13 +62,12 @@ def _run(cuda, kind, b, n, m, ns, c_pts, c_feat, n1, n2, seed):
         out_e = mlp.fused_sa_scale(kind, dp, df if df is not None else dp, foff, c, dc, di, dn, net)
         rm = [net[1].running_mean.double(), net[1].running_var.double(), net[4].running_mean.double(), net[4].running_var.double()]
         w1, g1, b1, w2, g2, b2 = [p_.detach() for p_ in params]
-        h1 = torch.relu((x.detach() @ w1.t() - rm[0]) / torch.sqrt(rm[1] + EPS) * g1 + b1)
-        z2 = torch.relu((h1 @ w2.t() - rm[2]) / torch.sqrt(rm[3] + EPS) * g2 + b2).view(-1, ns, n2).max(1).values
-    _check("eval out", out_e, z2)
-    fails = list(FAILS)
-    FAILS.clear()
+        h1 = torch.relu((x.detach() @ w1.t() - rm[0]) / torch.sqrt(rm[1] + sa_ref.EPS) * g1 + b1)
+        z2 = torch.relu((h1 @ w2.t() - rm[2]) / torch.sqrt(rm[3] + sa_ref.EPS) * g2 + b2).view(-1, ns, n2).max(1).values
+    sa_ref.check("eval out", out_e, z2)
+    fails = list(sa_ref.FAILS)
+    sa_ref.FAILS.clear()
     assert not fails, fails
-    return out
 
 
 @pytest.mark.parametrize("b,n,m,ns,c_pts,n2,seed", [(2, 500, 64, 16, 3, 64, 1), (3, 700, 40, 32, 4, 128, 2), (1, 300, 37, 8, 3, 64, 3),
