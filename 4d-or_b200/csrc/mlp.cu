@@ -223,6 +223,11 @@ struct RowGemmArgs {
     const float *E;          // EMODE 1: (R, N) pre-activation of the layer whose ReLU is differentiated
     const float *es, *et, *ei, *em;   // (N) each
     double *s1part;          // EMODE 3: (gridDim.x, 64, 8) per-CTA partial of S1
+    // column panels (gridDim.y > 1): CTA (x, y) computes output columns [y*N, (y+1)*N) of a wider layer
+    long long wimg_panel;    // floats between the weight images of two panels
+    long long partial_panel; // doubles between the statistics buffers of two panels
+    int ldg, lde;            // row strides of gsel / garg and of E (0 = N)
+    const float *bias;       // EMODE 2: added to every output row (N per panel) or nullptr
     int dbg_no_tma, dbg_no_mma, dbg_no_load, dbg_no_epi;   // ablation switches, honoured only in SG4D_DEBUG builds
 };
 
@@ -234,7 +239,8 @@ struct RowSmem {
     static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
     static constexpr int kCStride = N + 4;                  // padded fp32 row stride of the staged C tile
     static constexpr int kCBytes = kTileM * kCStride * 4;
-    static constexpr int kConst = 3 * 256 * 4;              // prologue constants s, t, p
+    static constexpr int kCF = 1280;                        // capacity (floats) of each prologue constant vector
+    static constexpr int kConst = 3 * kCF * 4;              // prologue constants s, t, p
     static constexpr int stages(int pmode) { return pmode == 2 ? 2 : kStg; }   // PMODE 2 gathers through L1: keep it large
     static constexpr int kXaBytes = kTileM * 8 * 4;         // EMODE 3: the tile's gathered rows [x | 1]
     static constexpr int kSaccBytes = 32 * kEpiThreads * 8; // EMODE 3: fp64 accumulators, 32 per epilogue thread
@@ -259,7 +265,7 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
     float *Cs = reinterpret_cast<float *>(smem + kStages * SM::kStageBytes);
     float *s_s = reinterpret_cast<float *>(smem + kStages * SM::kStageBytes + SM::kCBytes);
-    float *s_t = s_s + 256, *s_p = s_t + 256;
+    float *s_t = s_s + SM::kCF, *s_p = s_t + SM::kCF;
     __shared__ __align__(8) uint64_t s_bar[2 * 4 + 4];
     __shared__ uint32_t s_tmem;
 
@@ -267,6 +273,16 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
     const int K = p.op.ncols;
     const int nkb = (K + kKB - 1) / kKB;
     const long long ntiles = (p.R + kTileM - 1) / kTileM;
+    if (gridDim.y > 1) {   // column panel of a wider layer: shift everything that is indexed by output column
+        const int c0 = blockIdx.y * N;
+        p.wimg += (size_t)blockIdx.y * p.wimg_panel, p.ycol0 += c0;
+        if (p.partial) p.partial += (size_t)blockIdx.y * p.partial_panel;
+        if (p.gamma) p.gamma += c0;
+        if (p.gsel) p.gsel += c0, p.garg += c0;
+        if (p.E) p.E += c0, p.es += c0, p.et += c0, p.ei += c0, p.em += c0;
+        if (p.bias) p.bias += c0;
+    }
+    const int ldg = p.ldg ? p.ldg : N, lde = p.lde ? p.lde : N;
     const uint32_t bar_full = smem_u32(&s_bar[0]), bar_empty = smem_u32(&s_bar[kStages]);
     const uint32_t bar_tfull = smem_u32(&s_bar[2 * kStages]), bar_tempty = smem_u32(&s_bar[2 * kStages + 2]);
 
@@ -286,7 +302,7 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
         for (int k = tid; k < 512; k += kMlpThreads) s_s[k] = p.op.g.w1s[k];
         for (int k = tid; k < 64; k += kMlpThreads) s_p[k] = p.op.g.t1[k];
     } else if (PMODE != 0 && PMODE != 5)
-        for (int k = tid; k < 256; k += kMlpThreads) {
+        for (int k = tid; k < ((K + 31) & ~31); k += kMlpThreads) {
             s_s[k] = k < K ? p.op.s[k] : 0.f;
             s_t[k] = k < K ? p.op.t[k] : 0.f;
             s_p[k] = (PMODE == 3 && k < K) ? p.op.p[k] : 0.f;
@@ -590,7 +606,7 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int r = rb + u * kRowStep;
-                        ev[u] = r < nvalid ? __ldg(reinterpret_cast<const float4 *>(p.E + (row0 + r) * N + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        ev[u] = r < nvalid ? __ldg(reinterpret_cast<const float4 *>(p.E + (row0 + r) * lde + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -613,10 +629,13 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                 dacc[0] += a0.x, dacc[1] += a0.y, dacc[2] += a0.z, dacc[3] += a0.w;
                 dacc[4] += a1.x, dacc[5] += a1.y, dacc[6] += a1.z, dacc[7] += a1.w;
             } else if (p.Y) {   // coalesced store of the tile: 16 bytes per thread per step
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (EMODE == 2 && p.bias) bv = __ldg(reinterpret_cast<const float4 *>(p.bias + (e % kVecPerRow) * 4));   // kEpiThreads % kVecPerRow == 0: my columns are fixed
                 for (int v4 = e; v4 < nvalid * kVecPerRow; v4 += kEpiThreads) {
                     const int r = v4 / kVecPerRow, cc = (v4 % kVecPerRow) * 4;
-                    *reinterpret_cast<float4 *>(p.Y + (row0 + r) * p.ldy + p.ycol0 + cc) =
-                        *reinterpret_cast<const float4 *>(Cs + r * SM::kCStride + cc);
+                    float4 v = *reinterpret_cast<const float4 *>(Cs + r * SM::kCStride + cc);
+                    if (EMODE == 2) v.x += bv.x, v.y += bv.y, v.z += bv.z, v.w += bv.w;
+                    *reinterpret_cast<float4 *>(p.Y + (row0 + r) * p.ldy + p.ycol0 + cc) = v;
                 }
             }
             if (EMODE == 0) {   // per-channel statistics (+ group max/min) by the column owners
@@ -655,8 +674,8 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                             bi = take ? k0 + ix[0] : bi;
                             if (((r + 8) & smask) == 0) {             // last batch of the group (warp-uniform)
                                 const long long g = (row0 + r) >> p.logS;
-                                p.gsel[g * N + col] = best * sgn;
-                                p.garg[g * N + col] = (uint8_t)bi;
+                                p.gsel[g * ldg + col] = best * sgn;
+                                p.garg[g * ldg + col] = (uint8_t)bi;
                             }
                         }
                     }
@@ -675,8 +694,8 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                             bi = better ? k : bi;
                             if (k == smask) {
                                 const long long g = (row0 + r) >> p.logS;
-                                p.gsel[g * N + col] = best;
-                                p.garg[g * N + col] = (uint8_t)bi;
+                                p.gsel[g * ldg + col] = best;
+                                p.garg[g * ldg + col] = (uint8_t)bi;
                             }
                         }
                     }
@@ -735,8 +754,20 @@ struct WgradArgs {
     long long R;
     float *partial;          // (gridDim.x, 128, N)
     uint32_t d_lbo, d_sbo, d_type, d_kstep;   // MN-major descriptor fields (bytes / layout type)
+    // block grid (gridDim.y = mblocks * nnb): CTA (x, y) accumulates the (128 x N) block (y / nnb, y % nnb) of a larger dW
+    int nnb, mtot, ktot;
     int dbg_no_mma, dbg_no_load;
 };
+
+__device__ __forceinline__ void shift_operand(Operand &o, int c0, int total, int width) {
+    o.A += c0;
+    if (o.A2) o.A2 += c0;
+    if (o.s) o.s += c0;
+    if (o.t) o.t += c0;
+    if (o.p) o.p += c0;
+    if (o.dsel) o.dsel += c0, o.garg += c0;
+    o.ncols = max(0, min(width, total - c0));
+}
 
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t type) {
     uint64_t d = 0;
@@ -790,6 +821,12 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (gridDim.y > 1) {
+        const int mb = blockIdx.y / p.nnb, nb = blockIdx.y % p.nnb;
+        shift_operand(p.P, mb * kTileM, p.mtot, kTileM);
+        shift_operand(p.Q, nb * N, p.ktot, N);
+        p.partial += (size_t)blockIdx.y * gridDim.x * kTileM * N;
+    }
     const long long ntiles = (p.R + kTileM - 1) / kTileM;
     const long long per = (ntiles + gridDim.x - 1) / gridDim.x;
     const long long t_beg = min(ntiles, (long long)blockIdx.x * per), t_end = min(ntiles, t_beg + per);
@@ -1133,7 +1170,7 @@ pool_bwd_prologue_kernel(long long G, int N, int ldd, const float *__restrict__ 
 }
 
 template <int N, int PM, int EM, int PT>
-static int launch_row(const RowGemmArgs &a0, int grid, cudaStream_t stream) {
+static int launch_row(const RowGemmArgs &a0, int grid, cudaStream_t stream, int panels = 1) {
     RowGemmArgs a = a0;
 #ifdef SG4D_DEBUG   // ablation switches exist only in debug builds (a stray variable must never change production numerics)
     static const bool no_mma = getenv("SG4D_DBG_NOMMA") != nullptr, no_load = getenv("SG4D_DBG_NOLOAD") != nullptr;
@@ -1144,28 +1181,28 @@ static int launch_row(const RowGemmArgs &a0, int grid, cudaStream_t stream) {
     const int smem = RowSmem<N>::total(PM, EM);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return status_of(e);
-    kern<<<grid, PT + 32 + kEpiThreads, smem, stream>>>(a);
+    kern<<<dim3(grid, panels), PT + 32 + kEpiThreads, smem, stream>>>(a);
     return SG4D_LAUNCH_CHECK();
 }
 
 template <int PM, int EM>
-static int launch_row_n(int n, const RowGemmArgs &a, int grid, cudaStream_t stream) {
+static int launch_row_n(int n, const RowGemmArgs &a, int grid, cudaStream_t stream, int panels = 1) {
     // (measured in round 1: 16 producer warps do not pay for the row-tile kernels -- 80-register cap, epilogue-bound)
-    return n == 128 ? launch_row<128, PM, EM, 256>(a, grid, stream) : launch_row<64, PM, EM, 256>(a, grid, stream);
+    return n == 128 ? launch_row<128, PM, EM, 256>(a, grid, stream, panels) : launch_row<64, PM, EM, 256>(a, grid, stream, panels);
 }
 
 template <int N, int PM, int QM>
-static int launch_wgrad(const WgradArgs &a0, int grid, cudaStream_t stream) {
+static int launch_wgrad(const WgradArgs &a0, int grid, cudaStream_t stream, int blocks = 1) {
     WgradArgs a = a0;
 #ifdef SG4D_DEBUG
     static const bool no_mma = getenv("SG4D_DBG_NOMMA") != nullptr, no_load = getenv("SG4D_DBG_NOLOAD") != nullptr;
     a.dbg_no_mma = no_mma, a.dbg_no_load = no_load;
 #endif
-    auto kern = a.P.ncols <= 64 ? wgrad_kernel<N, PM, QM, 64> : wgrad_kernel<N, PM, QM, 128>;
+    auto kern = (a.P.ncols <= 64 && blocks == 1) ? wgrad_kernel<N, PM, QM, 64> : wgrad_kernel<N, PM, QM, 128>;
     const int smem = WgSmem<N>::total(PM);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return status_of(e);
-    kern<<<grid, kMlpThreadsT2, smem, stream>>>(a);
+    kern<<<dim3(grid, blocks), kMlpThreadsT2, smem, stream>>>(a);
     return SG4D_LAUNCH_CHECK();
 }
 
@@ -1234,15 +1271,19 @@ extern "C" int sg4d_pool_bwd_da(long long rows, int k, int n, int group, const f
                                 const float *dsel, const uint8_t *garg, const float *wimg_t, const float *y1,
                                 const float *es, const float *et, const float *ei, const float *em, float *dz1,
                                 double *partial, sg4d_stream_t stream) {
-    if (!row_common_ok(rows, k, k, n) || !pow2(group) || group > 128 || rows % group || !y2 || !a2 || !b2 || !dsel || !garg ||
-        !wimg_t || !y1 || !es || !et || !ei || !em || !dz1 || !partial)
+    // k = C2 (<= 1280), n = C1: 64, 128 or a multiple of 128 (column panels; wimg_t then is the dense image, and partial
+    // holds sg4d_dense_partial_doubles(rows, n) doubles)
+    if (rows <= 0 || k <= 0 || (k & 3) || k > RowSmem<128>::kCF || (n != 64 && (n & 127)) || !pow2(group) || group > 128 ||
+        rows % group || !y2 || !a2 || !b2 || !dsel || !garg || !wimg_t || !y1 || !es || !et || !ei || !em || !dz1 || !partial)
         return SG4D_EINVAL;
+    const int np = n == 64 ? 64 : 128;
     RowGemmArgs args{};
     args.op.A = y2, args.op.lda = k, args.op.s = a2, args.op.t = b2, args.op.dsel = dsel, args.op.garg = garg;
     args.op.S = group, args.op.logS = ilog2(group), args.op.ldsel = k, args.op.ncols = k;
     args.R = rows, args.wimg = wimg_t, args.Y = dz1, args.ldy = n, args.ycol0 = 0, args.partial = partial;
-    args.E = y1, args.es = es, args.et = et, args.ei = ei, args.em = em;
-    return launch_row_n<2, 1>(n, args, mlp_grid(rows), (cudaStream_t)stream);
+    args.wimg_panel = sg4d_weight_image_floats(np, k), args.partial_panel = sg4d_mlp_partial_doubles(rows);
+    args.E = y1, args.lde = n, args.es = es, args.et = et, args.ei = ei, args.em = em;
+    return launch_row_n<2, 1>(np, args, mlp_grid(rows), (cudaStream_t)stream, n / np);
 }
 
 extern "C" int sg4d_inner_bwd_dx(long long rows, int k, int n, const float *y1, const float *dz1, const float *p1,
@@ -1318,7 +1359,7 @@ extern "C" int sg4d_pool_bwd_prologue_parts(void) { return SG4D_NUM_SMS * 4; }
 extern "C" int sg4d_pool_bwd_prologue(long long groups, int n, int ldd, const float *d_out, const float *out,
                                       const float *gsel, const float *s2, const float *m2, const float *i2, float *dsel,
                                       double *partial, sg4d_stream_t stream) {
-    if (groups <= 0 || (n != 64 && n != 128) || ldd < n || (ldd & 3) || !d_out || !out || !gsel || !s2 || !m2 || !i2 || !dsel ||
+    if (groups <= 0 || (n != 64 && n != 128 && n != 256) || ldd < n || (ldd & 3) || !d_out || !out || !gsel || !s2 || !m2 || !i2 || !dsel ||
         !partial || (reinterpret_cast<uintptr_t>(d_out) & 15))
         return SG4D_EINVAL;
     pool_bwd_prologue_kernel<<<sg4d_pool_bwd_prologue_parts(), 256, 0, (cudaStream_t)stream>>>(groups, n, ldd, d_out, out, gsel,
@@ -1586,5 +1627,328 @@ extern "C" int sg4d_inner_bwd_dw_grouped(long long rows, int n, int m, int ns, i
     const int st = launch_wgrad<224, 3, 5>(args, grid, (cudaStream_t)stream);
     if (st != SG4D_OK) return st;
     wgrad_reduce_kernel<<<(mout * k + 255) / 256, 256, 0, (cudaStream_t)stream>>>(grid, mout, k, 224, partial, dw, lddw);
+    return SG4D_LAUNCH_CHECK();
+}
+
+// ================================================================================================
+// Dense layers on the same engine (the GroupAll level SA3, the TripletGCN MLPs, the classifier heads):
+//   Y (rows, n) = act(A) W^T [+ bias], n a multiple of 64, computed as column panels of 128 (or 64) by
+//   row_gemm_kernel (gridDim.y = panels); dW as (128 x 128) blocks by wgrad_kernel (gridDim.y = blocks).
+// Replaces nn.Linear / Conv2d(1x1) + BatchNorm + ReLU of OPS/pointnet2_modules.py:130-146,
+// SGH/model/gcns/network_TripletGCN.py:11-58 and SGH/model/pointnets/network_PointNet.py:188-271, which round 1 left
+// on cuBLAS / ATen.
+namespace sg4d {
+
+static int dense_panel(int n) { return (n % 128 == 0) ? 128 : 64; }
+
+// out = relu(y * s + t), float4
+__global__ void __launch_bounds__(256)
+bn_relu_apply_kernel(long long rows, int n4, const float *__restrict__ y, int ldy, const float *__restrict__ s,
+                     const float *__restrict__ t, float *__restrict__ out, int ldo) {
+    const long long total = rows * n4;
+    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const long long r = e / n4;
+        const int c = (int)(e - r * n4) * 4;
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(y + r * ldy + c));
+        const float4 sv = __ldg(reinterpret_cast<const float4 *>(s + c)), tv = __ldg(reinterpret_cast<const float4 *>(t + c));
+        float4 o;
+        o.x = fmaxf(fmaf(v.x, sv.x, tv.x), 0.f), o.y = fmaxf(fmaf(v.y, sv.y, tv.y), 0.f);
+        o.z = fmaxf(fmaf(v.z, sv.z, tv.z), 0.f), o.w = fmaxf(fmaf(v.w, sv.w, tv.w), 0.f);
+        *reinterpret_cast<float4 *>(out + r * ldo + c) = o;
+    }
+}
+
+// Backward prologue of [BatchNorm -> ReLU]: dz = dh .* [h > 0];  dzs = dz .* s;  per-column fp64 sums of dz and
+// dz .* (y - m) .* i.  One column group of 4 per thread, blockDim = (32 column groups, 8 row lanes); grid = (column
+// chunks of 128, row slices); every (row slice, column) partial is written once -> fixed-order final sum.
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_kernel(long long rows, int n, const float *__restrict__ dh, int lddh, const float *__restrict__ h, int ldh,
+                   const float *__restrict__ y, int ldy, const float *__restrict__ s, const float *__restrict__ m,
+                   const float *__restrict__ iv, float *__restrict__ dzs, int lddz, double *__restrict__ part) {
+    const int c = blockIdx.x * 128 + (threadIdx.x & 31) * 4, rl = threadIdx.x >> 5;
+    double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (c < n) {
+        const float4 sv = __ldg(reinterpret_cast<const float4 *>(s + c)), mv = __ldg(reinterpret_cast<const float4 *>(m + c));
+        const float4 ii = __ldg(reinterpret_cast<const float4 *>(iv + c));
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int since = 0;
+        for (long long r = (long long)blockIdx.y * 8 + rl; r < rows; r += (long long)gridDim.y * 8) {
+            const float4 d = __ldg(reinterpret_cast<const float4 *>(dh + r * lddh + c));
+            const float4 o = __ldg(reinterpret_cast<const float4 *>(h + r * ldh + c));
+            const float4 yy = __ldg(reinterpret_cast<const float4 *>(y + r * ldy + c));
+            float4 z;
+            z.x = o.x > 0.f ? d.x : 0.f, z.y = o.y > 0.f ? d.y : 0.f, z.z = o.z > 0.f ? d.z : 0.f, z.w = o.w > 0.f ? d.w : 0.f;
+            *reinterpret_cast<float4 *>(dzs + r * lddz + c) = make_float4(z.x * sv.x, z.y * sv.y, z.z * sv.z, z.w * sv.w);
+            a[0] += z.x, a[1] += z.y, a[2] += z.z, a[3] += z.w;
+            a[4] = fmaf(z.x, (yy.x - mv.x) * ii.x, a[4]), a[5] = fmaf(z.y, (yy.y - mv.y) * ii.y, a[5]);
+            a[6] = fmaf(z.z, (yy.z - mv.z) * ii.z, a[6]), a[7] = fmaf(z.w, (yy.w - mv.w) * ii.w, a[7]);
+            if (++since == 64) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc[u] += (double)a[u], a[u] = 0.f;
+                since = 0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] += (double)a[u];
+    }
+    __shared__ double sh[8][32][8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) sh[rl][threadIdx.x & 31][u] = acc[u];
+    __syncthreads();
+    if (rl == 0 && c < n) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            double t = 0.0;
+            for (int q = 0; q < 8; ++q) t += sh[q][threadIdx.x & 31][u];
+            // part layout: (2, gridDim.y, n): [0] = sum dz, [1] = sum dz * xhat
+            part[((size_t)(u >> 2) * gridDim.y + blockIdx.y) * n + c + (u & 3)] = t;
+        }
+    }
+}
+
+// out[j][c] = sum over slices of part[j][slice][c]   (j = 0, 1)
+__global__ void colsum_final_kernel(int n, int slices, const double *__restrict__ part, float *__restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n) return;
+    const int j = t / n, c = t % n;
+    double a = 0.0;
+    for (int q = 0; q < slices; ++q) a += part[((size_t)j * slices + q) * n + c];
+    out[t] = (float)a;
+}
+
+// column sums of a (rows, n) matrix (bias gradients): same two-stage scheme, single quantity
+__global__ void __launch_bounds__(256)
+colsum_kernel(long long rows, int n, const float *__restrict__ a, int lda, double *__restrict__ part) {
+    const int c = blockIdx.x * 128 + (threadIdx.x & 31) * 4, rl = threadIdx.x >> 5;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    if (c < n)
+        for (long long r = (long long)blockIdx.y * 8 + rl; r < rows; r += (long long)gridDim.y * 8) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(a + r * lda + c));
+            acc[0] += v.x, acc[1] += v.y, acc[2] += v.z, acc[3] += v.w;
+        }
+    __shared__ double sh[8][32][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sh[rl][threadIdx.x & 31][u] = acc[u];
+    __syncthreads();
+    if (rl == 0 && c < n)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            double t = 0.0;
+            for (int q = 0; q < 8; ++q) t += sh[q][threadIdx.x & 31][u];
+            part[(size_t)blockIdx.y * n + c + u] = t;
+            part[((size_t)gridDim.y + blockIdx.y) * n + c + u] = 0.0;
+        }
+}
+
+// BatchNorm finalize over column panels: channel c lives in panel c / np, thread slot c % np of every epilogue thread group
+__global__ void dense_bn_finalize_kernel(int n, int np, int pairs_per_panel, long long R, const double *__restrict__ partial,
+                                         const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
+                                         float momentum, float *running_mean, float *running_var, float *__restrict__ stats) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= n) return;
+    double s, q;
+    warp_sum_pairs(c % np, np, pairs_per_panel, partial + (size_t)(c / np) * pairs_per_panel * 2, s, q);
+    if (threadIdx.x & 31) return;
+    const double mean = s / (double)R;
+    double var = q / (double)R - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    stats[c] = sc, stats[n + c] = beta[c] - (float)mean * sc, stats[2 * n + c] = (float)mean, stats[3 * n + c] = invstd;
+    if (running_mean) {
+        const double unbiased = R > 1 ? var * (double)R / (double)(R - 1) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+// dW[m, k] from the per-(block, CTA) partials of a block-grid wgrad launch
+__global__ void __launch_bounds__(256)
+dense_wgrad_reduce_kernel(int nparts, int mtot, int ktot, int nb_width, int nnb, const float *__restrict__ partial,
+                          float *__restrict__ dw, int lddw) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= mtot * ktot) return;
+    const int m = t / ktot, k = t % ktot;
+    const int blk = (m / kTileM) * nnb + k / nb_width;
+    const float *src = partial + ((size_t)blk * nparts * kTileM + (m % kTileM)) * nb_width + (k % nb_width);
+    double acc = 0.0;
+    for (int c = 0; c < nparts; ++c) acc += (double)src[(size_t)c * kTileM * nb_width];
+    dw[(size_t)m * lddw + k] = (float)acc;
+}
+
+template <int PM, int QM>
+static int launch_dense_wgrad(const WgradArgs &a0, int grid, int blocks, cudaStream_t stream) {
+    WgradArgs a = a0;
+    auto kern = wgrad_kernel<128, PM, QM, 128>;
+    const int smem = WgSmem<128>::total(PM);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return status_of(e);
+    kern<<<dim3(grid, blocks), kMlpThreadsT2, smem, stream>>>(a);
+    return SG4D_LAUNCH_CHECK();
+}
+
+}  // namespace sg4d
+
+extern "C" long long sg4d_dense_weight_floats(int n, int k) {
+    const int np = dense_panel(n);
+    return (long long)(n / np) * sg4d_weight_image_floats(np, k);
+}
+
+extern "C" int sg4d_dense_pack_weight(int n, int k, int ldw, const float *w, float *img, sg4d_stream_t stream) {
+    if (n <= 0 || (n & 63) || k <= 0 || ldw < k || !w || !img) return SG4D_EINVAL;
+    const int np = dense_panel(n);
+    const long long per = sg4d_weight_image_floats(np, k);
+    for (int pnl = 0; pnl < n / np; ++pnl) {
+        const int st = sg4d_pack_weight(np, k, ldw, w + (size_t)pnl * np * ldw, img + (size_t)pnl * per, stream);
+        if (st != SG4D_OK) return st;
+    }
+    return SG4D_OK;
+}
+
+extern "C" long long sg4d_dense_partial_doubles(long long rows, int n) {
+    return (long long)(n / dense_panel(n)) * sg4d_mlp_partial_doubles(rows);
+}
+
+static bool dense_ok(long long rows, int k, int lda, int n, const void *a, int ldy) {
+    return rows > 0 && k > 0 && !(k & 3) && lda >= k && !(lda & 3) && n > 0 && !(n & 63) && a && ldy >= n && !(ldy & 3) &&
+           !(reinterpret_cast<uintptr_t>(a) & 15);
+}
+
+extern "C" int sg4d_dense_fwd(long long rows, int k, int lda, int n, const float *a, const float *scale, const float *shift,
+                              const float *wimg, const float *bias, float *y, int ldy, double *partial, int group,
+                              const float *gamma, float *gsel, uint8_t *garg, sg4d_stream_t stream) {
+    if (!dense_ok(rows, k, lda, n, a, ldy) || !wimg || !y || (scale && (!shift || k > RowSmem<128>::kCF)) || (partial && bias))
+        return SG4D_EINVAL;
+    const int np = dense_panel(n);
+    if (group != 0 && (!partial || group < 1 || (128 % group) || group > kTileM / (kEpiThreads / np) || rows % group || !gamma || !gsel || !garg))
+        return SG4D_EINVAL;
+    RowGemmArgs args{};
+    args.op.A = a, args.op.lda = lda, args.op.s = scale, args.op.t = shift, args.op.ncols = k;
+    args.R = rows, args.wimg = wimg, args.Y = y, args.ldy = ldy, args.ycol0 = 0, args.partial = partial;
+    args.wimg_panel = sg4d_weight_image_floats(np, k), args.partial_panel = sg4d_mlp_partial_doubles(rows);
+    args.S = group, args.logS = group ? ilog2(group) : 0, args.gamma = gamma, args.gsel = gsel, args.garg = garg, args.ldg = n;
+    args.bias = bias;
+    const int grid = mlp_grid(rows), panels = n / np;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (partial) return scale ? launch_row_n<1, 0>(np, args, grid, st, panels) : launch_row_n<0, 0>(np, args, grid, st, panels);
+    return scale ? launch_row_n<1, 2>(np, args, grid, st, panels) : launch_row_n<0, 2>(np, args, grid, st, panels);
+}
+
+extern "C" int sg4d_dense_bn_finalize(int n, long long rows, const double *partial, const float *gamma, const float *beta,
+                                      float eps, float momentum, float *running_mean, float *running_var, float *stats,
+                                      sg4d_stream_t stream) {
+    if (n <= 0 || (n & 63) || rows <= 0 || !partial || !gamma || !beta || !stats) return SG4D_EINVAL;
+    dense_bn_finalize_kernel<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(n, dense_panel(n), mlp_grid(rows) * kEpiThreads, rows,
+                                                                             partial, gamma, beta, eps, momentum, running_mean,
+                                                                             running_var, stats);
+    return SG4D_LAUNCH_CHECK();
+}
+
+extern "C" int sg4d_bn_relu_apply(long long rows, int n, const float *y, int ldy, const float *scale, const float *shift,
+                                  float *out, int ldo, sg4d_stream_t stream) {
+    if (rows <= 0 || n <= 0 || (n & 3) || (ldy & 3) || (ldo & 3) || !y || !scale || !shift || !out) return SG4D_EINVAL;
+    const long long total = rows * (n / 4);
+    long long g = (total + 255) / 256;
+    if (g > SG4D_NUM_SMS * 16) g = SG4D_NUM_SMS * 16;
+    bn_relu_apply_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(rows, n / 4, y, ldy, scale, shift, out, ldo);
+    return SG4D_LAUNCH_CHECK();
+}
+
+static int colsum_slices(long long rows) {
+    long long s = (rows + 255) / 256;
+    return (int)(s < 1 ? 1 : (s > 64 ? 64 : s));
+}
+extern "C" long long sg4d_colsum_part_doubles(long long rows, int n) { return 2LL * colsum_slices(rows) * n; }
+
+extern "C" int sg4d_bn_relu_bwd(long long rows, int n, const float *dh, int lddh, const float *h, int ldh, const float *y,
+                                int ldy, const float *stats, float *dzs, int lddz, double *part, float *sums,
+                                sg4d_stream_t stream) {
+    if (rows <= 0 || n <= 0 || (n & 3) || (lddh & 3) || (ldh & 3) || (ldy & 3) || (lddz & 3) || !dh || !h || !y || !stats || !dzs ||
+        !part || !sums)
+        return SG4D_EINVAL;
+    const int slices = colsum_slices(rows);
+    bn_relu_bwd_kernel<<<dim3((n + 127) / 128, slices), 256, 0, (cudaStream_t)stream>>>(rows, n, dh, lddh, h, ldh, y, ldy, stats,
+                                                                                         stats + 2 * n, stats + 3 * n, dzs, lddz, part);
+    colsum_final_kernel<<<(2 * n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, slices, part, sums);
+    return SG4D_LAUNCH_CHECK();
+}
+
+extern "C" int sg4d_colsum(long long rows, int n, const float *a, int lda, double *part, float *out, sg4d_stream_t stream) {
+    if (rows <= 0 || n <= 0 || (n & 3) || (lda & 3) || !a || !part || !out) return SG4D_EINVAL;
+    const int slices = colsum_slices(rows);
+    colsum_kernel<<<dim3((n + 127) / 128, slices), 256, 0, (cudaStream_t)stream>>>(rows, n, a, lda, part);
+    colsum_final_kernel<<<(2 * n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, slices, part, out);   // out: (2, n), second row zeros
+    return SG4D_LAUNCH_CHECK();
+}
+
+// dX (rows, nout) = dY * W  [.* [E*es + et > 0]]  with dY = a (mode 0) or a2 .* p - (a .* q + u) (mode 3); kk = columns
+// of dY (<= 1280 for mode 3), wimg_t = dense image of W^T (nout x kk).
+extern "C" int sg4d_dense_bwd_dx(long long rows, int kk, int lda, int nout, int mode, const float *a, const float *a2,
+                                 const float *p1, const float *q1, const float *u1, const float *wimg_t, const float *e,
+                                 int lde, const float *es, const float *et, float *dx, int lddx, double *partial,
+                                 sg4d_stream_t stream) {
+    if (!dense_ok(rows, kk, lda, nout, a, lddx) || !wimg_t || !dx || (mode != 0 && mode != 3) ||
+        (mode == 3 && (!a2 || !p1 || !q1 || !u1 || kk > RowSmem<128>::kCF)) || (e && (!es || !et || !partial || lde < nout)))
+        return SG4D_EINVAL;
+    const int np = dense_panel(nout);
+    RowGemmArgs args{};
+    args.op.A = a, args.op.lda = lda, args.op.A2 = a2, args.op.lda2 = lda, args.op.s = q1, args.op.t = u1, args.op.p = p1;
+    args.op.ncols = kk;
+    args.R = rows, args.wimg = wimg_t, args.Y = dx, args.ldy = lddx, args.ycol0 = 0, args.partial = partial;
+    args.wimg_panel = sg4d_weight_image_floats(np, kk), args.partial_panel = sg4d_mlp_partial_doubles(rows);
+    args.E = e, args.lde = lde, args.es = es, args.et = et, args.ei = es, args.em = et;
+    const int grid = mlp_grid(rows), panels = nout / np;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 0) return e ? launch_row_n<0, 1>(np, args, grid, st, panels) : launch_row_n<0, 2>(np, args, grid, st, panels);
+    return e ? launch_row_n<3, 1>(np, args, grid, st, panels) : launch_row_n<3, 2>(np, args, grid, st, panels);
+}
+
+extern "C" long long sg4d_dense_wgrad_partial_floats(long long rows, int m, int k) {
+    return (long long)((m + 127) / 128) * ((k + 127) / 128) * mlp_grid(rows) * kTileM * 128;
+}
+
+// dW (m x k, row stride lddw) = dY^T * act(x);  dY (rows, m) as in sg4d_dense_bwd_dx;  act(x) = x or relu(x .* xs + xt)
+extern "C" int sg4d_dense_bwd_dw(long long rows, int m, int lda, int k, int mode, const float *a, const float *a2,
+                                 const float *p1, const float *q1, const float *u1, const float *x, int ldx, const float *xs,
+                                 const float *xt, float *partial, float *dw, int lddw, sg4d_stream_t stream) {
+    if (rows <= 0 || m <= 0 || (m & 3) || k <= 0 || (k & 3) || lda < m || (lda & 3) || ldx < k || (ldx & 3) || !a || !x || !partial ||
+        !dw || lddw < k || (mode != 0 && mode != 3) || (mode == 3 && (!a2 || !p1 || !q1 || !u1)) || (xs && !xt))
+        return SG4D_EINVAL;
+    WgradArgs args{};
+    args.P.A = a, args.P.lda = lda, args.P.A2 = a2, args.P.lda2 = lda, args.P.s = q1, args.P.t = u1, args.P.p = p1, args.P.ncols = m;
+    args.Q.A = x, args.Q.lda = ldx, args.Q.s = xs, args.Q.t = xt, args.Q.ncols = k;
+    const int grid = mlp_grid(rows), mb = (m + 127) / 128, nnb = (k + 127) / 128;
+    args.R = rows, args.partial = partial, args.nnb = nnb, args.mtot = m, args.ktot = k;
+    args.d_lbo = 4096, args.d_sbo = 512, args.d_type = 1, args.d_kstep = 1024;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (mb * nnb == 1) {   // single block: the kernel's un-shifted path needs the clamps applied here
+        args.P.ncols = m < 128 ? m : 128, args.Q.ncols = k < 128 ? k : 128;
+    }
+    if (mode == 0) rc = xs ? launch_dense_wgrad<0, 1>(args, grid, mb * nnb, st) : launch_dense_wgrad<0, 0>(args, grid, mb * nnb, st);
+    else rc = xs ? launch_dense_wgrad<3, 1>(args, grid, mb * nnb, st) : launch_dense_wgrad<3, 0>(args, grid, mb * nnb, st);
+    if (rc != SG4D_OK) return rc;
+    dense_wgrad_reduce_kernel<<<(m * k + 255) / 256, 256, 0, st>>>(grid, m, k, 128, nnb, partial, dw, lddw);
+    return SG4D_LAUNCH_CHECK();
+}
+
+// dW2 (m x n) = dY2^T * relu(y1 .* s1 + t1) for wide layers (m, n multiples of 4; 128 x 128 blocks, one launch);
+// dY2 as in sg4d_pool_bwd_da.  partial: sg4d_dense_wgrad_partial_floats(rows, m, n).
+extern "C" int sg4d_dense_pool_bwd_dw(long long rows, int m, int n, int group, const float *y2, const float *a2,
+                                      const float *b2, const float *dsel, const uint8_t *garg, const float *y1,
+                                      const float *s1, const float *t1, float *partial, float *dw, sg4d_stream_t stream) {
+    if (rows <= 0 || m <= 0 || (m & 3) || n <= 0 || (n & 3) || !pow2(group) || group > 128 || rows % group || !y2 || !a2 || !b2 ||
+        !dsel || !garg || !y1 || !s1 || !t1 || !partial || !dw)
+        return SG4D_EINVAL;
+    WgradArgs args{};
+    args.P.A = y2, args.P.lda = m, args.P.s = a2, args.P.t = b2, args.P.dsel = dsel, args.P.garg = garg, args.P.S = group;
+    args.P.logS = ilog2(group), args.P.ldsel = m, args.P.ncols = m < 128 ? m : 128;
+    args.Q.A = y1, args.Q.lda = n, args.Q.s = s1, args.Q.t = t1, args.Q.ncols = n < 128 ? n : 128;
+    const int grid = mlp_grid(rows), mb = (m + 127) / 128, nnb = (n + 127) / 128;
+    args.R = rows, args.partial = partial, args.nnb = nnb, args.mtot = m, args.ktot = n;
+    args.d_lbo = 4096, args.d_sbo = 512, args.d_type = 1, args.d_kstep = 1024;
+    const int rc = launch_dense_wgrad<2, 1>(args, grid, mb * nnb, (cudaStream_t)stream);
+    if (rc != SG4D_OK) return rc;
+    dense_wgrad_reduce_kernel<<<(m * n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(grid, m, n, 128, nnb, partial, dw, n);
     return SG4D_LAUNCH_CHECK();
 }

@@ -5,6 +5,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import dense
+
 
 def _init_head(module):
     # BaseNetwork.init_weights('xavier_normal', 1) as called by the reference heads
@@ -37,15 +39,14 @@ class PointNetCls(nn.Module):
             _init_head(self)
 
     def forward(self, x):
-        x = self.fc1(x)
         if self.use_batch_norm:
-            x = self.bn1(x)
-        x = self.fc2(self.relu(x))
+            raise NotImplementedError("sg4d heads: batch_norm=True has no kernel path (the reference builds its heads "
+                                      "with batch_norm=False, scene_graph_prediction_model.py:65-72)")
+        x = dense.linear(x, self.fc1)
+        x = dense.linear(x, self.fc2, pre_relu=True)          # the ReLU is fused into the operand stager
         if self.use_drop_out:
             x = self.dropout(x)
-        if self.use_batch_norm:
-            x = self.bn2(x)
-        return F.log_softmax(self.fc3(self.relu(x)), dim=1)
+        return F.log_softmax(dense.linear(x, self.fc3, pre_relu=True), dim=1)
 
 
 class PointNetRelCls(nn.Module):
@@ -68,14 +69,13 @@ class PointNetRelCls(nn.Module):
             _init_head(self)
 
     def forward(self, x, relation_objects_one_hot=None, image_embeddings=None):
-        x = self.fc1(x)
         if self.use_bn:
-            x = self.bn1(x)
-        x = self.fc2(self.relu(x))
+            raise NotImplementedError("sg4d heads: batch_norm=True has no kernel path (the reference builds its heads "
+                                      "with batch_norm=False, scene_graph_prediction_model.py:65-72)")
+        x = dense.linear(x, self.fc1)
+        x = dense.linear(x, self.fc2, pre_relu=True)          # the ReLU is fused into the operand stager
         if self.use_drop_out:
             x = self.dropout(x)
-        if self.use_bn:
-            x = self.bn2(x)
         x = self.relu(x)
         if image_embeddings is not None:  # late fusion (:265-267)
             if image_embeddings.dim() == 1:  # one scene: the same embedding for every edge
@@ -83,4 +83,4 @@ class PointNetRelCls(nn.Module):
             x = torch.cat([x, image_embeddings], dim=1)
         if relation_objects_one_hot is not None:
             x = torch.cat([x, relation_objects_one_hot], dim=1)
-        return F.log_softmax(self.fc3(x), dim=1)
+        return F.log_softmax(dense.linear(x, self.fc3), dim=1)

@@ -9,7 +9,7 @@ linears; ``nn2``: 512->512 (+BN+ReLU) ->256) and the same maths as the reference
 import torch
 import torch.nn as nn
 
-from .. import rows
+from .. import dense, rows
 
 
 def build_mlp(dim_list, activation='relu', do_bn=False, dropout=0, on_last=False):
@@ -39,13 +39,34 @@ class TripletGCN(nn.Module):
                              do_bn=use_bn, on_last=True)
         self.nn2 = build_mlp([dim_hidden, dim_hidden, dim_node], do_bn=use_bn)
 
+    @staticmethod
+    def _run(seq, x):
+        """A ``build_mlp`` stack on the tensor-core engine (sg4d.dense): Linear -> BatchNorm1d -> ReLU blocks as fused
+        GEMM + statistics + backward-in-the-stager kernels, a trailing plain Linear with its bias in the GEMM epilogue."""
+        layers = list(seq)
+        i = 0
+        while i < len(layers):
+            lin = layers[i]
+            if not isinstance(lin, nn.Linear):
+                raise NotImplementedError(f"TripletGCN MLP: unexpected layer {type(lin).__name__}")
+            if i + 2 < len(layers) and isinstance(layers[i + 1], nn.BatchNorm1d) and isinstance(layers[i + 2], nn.ReLU):
+                x = dense.linear_bn_relu(x, lin, layers[i + 1])
+                i += 3
+            elif i + 1 == len(layers):
+                x = dense.linear(x, lin)
+                i += 1
+            else:
+                raise NotImplementedError("TripletGCN MLP: only [Linear, BatchNorm1d, ReLU] blocks and a final Linear "
+                                          "(use_bn=True, activation='relu', dropout=0: what the reference builds)")
+        return x
+
     def forward(self, x, edge_feature, edge_index, csr=None):
         if csr is None:
             csr = rows.EdgeCSR(edge_index, x.shape[0])
-        h = self.nn1(rows.triplet_gather(x, edge_feature, csr))          # (E, 2*hidden + edge)
+        h = self._run(self.nn1, rows.triplet_gather(x, edge_feature, csr))     # (E, 2*hidden + edge)
         new_e = h[:, self.dim_hidden:self.dim_hidden + self.dim_edge]
-        m = rows.message_aggregate(h, self.dim_hidden, self.dim_edge, csr)  # sum over incoming edges
-        return self.nn2(m), new_e
+        m = rows.message_aggregate(h, self.dim_hidden, self.dim_edge, csr)      # sum over incoming edges
+        return self._run(self.nn2, m), new_e
 
 
 class TripletGCNModel(nn.Module):

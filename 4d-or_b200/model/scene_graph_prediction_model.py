@@ -24,6 +24,7 @@ import torch.nn.functional as F
 import torch.optim as optim
 from torch import nn
 
+from .. import dense
 from .network_PointNet import PointNetCls, PointNetRelCls
 from .network_PointNet2 import PointNetfeat
 from .network_TripletGCN import TripletGCNModel
@@ -91,7 +92,8 @@ class SGPNModelWrapper(nn.Module):
         obj_cls = self.obj_predictor(gcn_obj_feature if self.mconfig['OBJ_PRED_FROM_GCN'] else obj_feature)
         image_embeddings = None
         if self.use_image:
-            feats = self.full_image_feature_reduction(batch['full_image_features'])
+            fi = batch['full_image_features']
+            feats = dense.linear(fi.reshape(-1, fi.shape[-1]), self.full_image_feature_reduction).reshape(*fi.shape[:-1], -1)
             if feats.dim() == 2:            # one scene: (6, 128) -> (768,)
                 image_embeddings = feats.flatten()
             else:                           # S scenes: (S, 6, 128) -> per-edge (E, 768)

@@ -5,8 +5,9 @@
 ``forward(xyz, features)`` keeps the reference contract (xyz (B,N,3), features (B,C,N) ->
 new_xyz (B,npoint,3), new_features (B,sum C_out,npoint)).  Internally everything runs point-major
 through ``forward_rows``: one FPS launch that also emits the picked centres, one ball-query launch
-for all radii of the level, one fused group+recentre+concat launch per scale, then the shared MLP
-on (rows, channels) matrices and a max over the nsample rows of each centre.  The shared MLP is
+for all radii of the level, then per scale the fused tensor-core kernels
+that go from the ball-query indices to the pooled features (``mlp.fused_sa_scale``; other shapes: grouped rows +
+``dense.pooled_shared_mlp``).  The shared MLP is
 still ``[1x1 conv -> BatchNorm2d -> ReLU] x L`` (modules.py:9-19) evaluated on the same values --
 a 1x1 convolution over (B,C,npoint,nsample) IS a matrix product over rows -- so parameters,
 running statistics and results match the reference module.
@@ -17,6 +18,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import dense
 from .. import mlp as fused
 from .. import rows
 from . import pointnet2_utils
@@ -30,36 +32,6 @@ def build_shared_mlp(mlp_spec: List[int], bn: bool = True):
             layers.append(nn.BatchNorm2d(c_out))
         layers.append(nn.ReLU(True))
     return nn.Sequential(*layers)
-
-
-def _batch_norm_rows(bn, x):
-    """nn.BatchNorm2d.forward on a (rows, C) matrix: statistics over rows == over (B, H, W)."""
-    use_batch_stats = bn.training or not bn.track_running_stats
-    momentum = 0.0 if bn.momentum is None else bn.momentum
-    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
-        if bn.momentum is None:
-            momentum = 1.0 / float(bn.num_batches_tracked)
-    return F.batch_norm(x, bn.running_mean if (not bn.training or bn.track_running_stats) else None,
-                        bn.running_var if (not bn.training or bn.track_running_stats) else None,
-                        bn.weight, bn.bias, use_batch_stats, momentum, bn.eps)
-
-
-def shared_mlp_rows(mlp: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
-    """Apply a ``build_shared_mlp`` stack to x (rows, K_padded); extra zero columns are ignored."""
-    for layer in mlp:
-        if isinstance(layer, nn.Conv2d):
-            w = layer.weight.view(layer.out_channels, layer.in_channels)
-            if x.shape[1] != w.shape[1]:
-                w = F.pad(w, (0, x.shape[1] - w.shape[1]))
-            x = F.linear(x, w, layer.bias)
-        elif isinstance(layer, nn.BatchNorm2d):
-            x = _batch_norm_rows(layer, x)
-        elif isinstance(layer, nn.ReLU):
-            x = F.relu(x, inplace=True)
-        else:
-            raise TypeError(f"unexpected layer in shared MLP: {type(layer).__name__}")
-    return x
 
 
 def _pad4(k):
@@ -84,13 +56,24 @@ class _PointnetSAModuleBase(nn.Module):
         b, n = pts.shape[0], pts.shape[1]
         outs = []
         if self.npoint is None:  # GroupAll (utils.py:353-383): xyz not recentred, one group of n points
-            cols = [pts[:, :, :3]]
-            if feats is not None and c > 0:
-                cols.append(feats[:, :, feat_offset:feat_offset + c])
-            x = torch.cat(cols, dim=2) if self.groupers[0].use_xyz or feats is None else cols[1]
+            if not self.groupers[0].use_xyz and feats is None:
+                raise RuntimeError("GroupAll without xyz needs features")
+            needs_dx = feats is not None and feats.requires_grad and torch.is_grad_enabled()
+            if n not in (1, 2, 4, 8, 16, 32, 64, 128):
+                raise NotImplementedError(f"GroupAll over {n} points: the fused max-pool needs a power of two <= 128")
+            f = feats[:, :, feat_offset:feat_offset + c] if feats is not None and c > 0 else None
+            use_xyz = self.groupers[0].use_xyz or f is None
+            k = (3 if use_xyz else 0) + (c if f is not None else 0)
+            pad = pts.new_zeros(b, n, _pad4(k) - k)
+            # feature-first columns when a gradient flows back (16-byte aligned dX); the weight columns are permuted to match
+            xyz_last = needs_dx and use_xyz
+            cols = ([f] if f is not None else []) + ([pts[:, :, :3]] if use_xyz else []) if xyz_last else \
+                   ([pts[:, :, :3]] if use_xyz else []) + ([f] if f is not None else [])
+            x = torch.cat(cols + [pad], dim=2).reshape(b * n, _pad4(k))
             for mlp in self.mlps:
-                y = shared_mlp_rows(mlp, x.reshape(b * n, x.shape[2]))
-                outs.append(y.view(b, n, -1).amax(dim=1, keepdim=True))
+                if not use_xyz:
+                    raise NotImplementedError("GroupAll with use_xyz=False")
+                outs.append(dense.pooled_shared_mlp(x, k, n, mlp, xyz_last).view(b, 1, -1))
             return None, torch.cat(outs, dim=2) if len(outs) > 1 else outs[0]
 
         # large clouds: one spatial index (Morton-sorted copy + bucket boxes) serves both FPS and the ball query
@@ -99,7 +82,7 @@ class _PointnetSAModuleBase(nn.Module):
         radii = [g.radius for g in self.groupers]
         nsamples = [g.nsample for g in self.groupers]
         if index is not None and max(nsamples) > 64:
-            index = None
+            raise NotImplementedError("ball query through the spatial index keeps up to 64 samples per centre")
         idx, cnt = rows.ball_query_rows(new_xyz, pts, radii, nsamples, index)
         needs_dx = feats is not None and feats.requires_grad and torch.is_grad_enabled()
         for s, mlp in enumerate(self.mlps):
@@ -112,18 +95,11 @@ class _PointnetSAModuleBase(nn.Module):
                 outs.append(fused.fused_sa_scale(kind, pts, feats, feat_offset, c, new_xyz, idx[s], cnt[s], mlp)
                             .view(b, self.npoint, -1))
                 continue
+            # any other shape: materialised grouped rows + the generic tensor-core MLP (zero-padded widths); no PyTorch path
             stride = 8 if k <= 8 else _pad4(k)
-            use_fused = fused.supported(mlp, stride, nsamples[s]) and (not needs_dx or c % 64 == 0)
-            # feature-first column order when a gradient flows back into the gathered features (aligned dX)
-            xyz_last = use_fused and needs_dx
+            xyz_last = needs_dx                 # feature-first columns when a gradient flows back (aligned dX)
             x = rows.group_rows(pts, feats, new_xyz, idx[s], cnt[s], c, feat_offset, stride, xyz_last)
-            if use_fused:
-                # tensor-core path: conv+BN+ReLU x2 + max-pool, forward and backward (csrc/mlp.cu)
-                outs.append(fused.fused_shared_mlp(x.view(-1, stride), k, nsamples[s], mlp, xyz_last)
-                            .view(b, self.npoint, -1))
-            else:
-                y = shared_mlp_rows(mlp, x.view(-1, stride))
-                outs.append(y.view(b * self.npoint, nsamples[s], -1).amax(dim=1).view(b, self.npoint, -1))
+            outs.append(dense.pooled_shared_mlp(x.view(-1, stride), k, nsamples[s], mlp, xyz_last).view(b, self.npoint, -1))
         return new_xyz, torch.cat(outs, dim=2) if len(outs) > 1 else outs[0]
 
     def forward(self, xyz: torch.Tensor, features: Optional[torch.Tensor]

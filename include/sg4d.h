@@ -332,6 +332,54 @@ int sg4d_inner_bwd_dw_grouped(long long rows, int n, int m, int ns, int pstride,
                               const float *y1, const float *dz1, const float *p1, const float *q1, const float *u1,
                               float *partial, float *dw, int lddw, sg4d_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Section 5 -- dense layers on the same tensor-core engine: the GroupAll level SA3 (OPS/pointnet2_modules.py:130-146),
+ * the TripletGCN MLPs (SGH/model/gcns/network_TripletGCN.py:11-58) and the classifier heads
+ * (SGH/model/pointnets/network_PointNet.py:188-271).  n = output channels, a multiple of 64 (the host pads narrower
+ * layers); wide layers run as column panels of 128 (64 if n % 128 != 0) in ONE launch.
+ * ---------------------------------------------------------------------------------------------- */
+long long sg4d_dense_weight_floats(int n, int k);
+int sg4d_dense_pack_weight(int n, int k, int ldw, const float *w, float *img, sg4d_stream_t stream);
+long long sg4d_dense_partial_doubles(long long rows, int n);
+/* y (rows, n; row stride ldy) = act(a) * W^T [+ bias];  act = identity (scale NULL) or relu(a .* scale + shift) (k <= 1280).
+ * partial != NULL: also the per-channel sum / sum of squares for sg4d_dense_bn_finalize (bias must be NULL: a bias in
+ * front of a BatchNorm cancels) and, with group > 0, the fused max/min over groups of rows exactly like sg4d_linear_fwd
+ * (gsel / garg: (rows / group, n)). */
+int sg4d_dense_fwd(long long rows, int k, int lda, int n, const float *a, const float *scale, const float *shift,
+                   const float *wimg, const float *bias, float *y, int ldy, double *partial, int group, const float *gamma,
+                   float *gsel, uint8_t *garg, sg4d_stream_t stream);
+/* stats (4, n) = scale, shift, mean, invstd (nn.BatchNorm1d / BatchNorm2d batch statistics; running_* updated when given) */
+int sg4d_dense_bn_finalize(int n, long long rows, const double *partial, const float *gamma, const float *beta, float eps,
+                           float momentum, float *running_mean, float *running_var, float *stats, sg4d_stream_t stream);
+/* out = relu(y .* scale + shift) */
+int sg4d_bn_relu_apply(long long rows, int n, const float *y, int ldy, const float *scale, const float *shift, float *out,
+                       int ldo, sg4d_stream_t stream);
+/* Backward prologue of [BatchNorm -> ReLU]: dz = dh .* [h > 0]; dzs = dz .* scale; sums (2, n) = (sum dz, sum dz .* xhat)
+ * = (d_beta, d_gamma).  part: sg4d_colsum_part_doubles(rows, n) doubles of scratch. */
+long long sg4d_colsum_part_doubles(long long rows, int n);
+int sg4d_bn_relu_bwd(long long rows, int n, const float *dh, int lddh, const float *h, int ldh, const float *y, int ldy,
+                     const float *stats, float *dzs, int lddz, double *part, float *sums, sg4d_stream_t stream);
+/* out (2, n): row 0 = column sums of a (bias gradients), row 1 = 0 */
+int sg4d_colsum(long long rows, int n, const float *a, int lda, double *part, float *out, sg4d_stream_t stream);
+/* dX (rows, nout) = dY * W [.* [e .* es + et > 0]];  dY (rows, kk) = a (mode 0) or a2 .* p1 - (a .* q1 + u1) (mode 3, the
+ * BatchNorm backward evaluated in the operand stagers);  wimg_t = sg4d_dense_pack_weight of W^T (nout x kk);
+ * partial (sg4d_dense_partial_doubles(rows, nout)) is scratch, required with e. */
+int sg4d_dense_bwd_dx(long long rows, int kk, int lda, int nout, int mode, const float *a, const float *a2, const float *p1,
+                      const float *q1, const float *u1, const float *wimg_t, const float *e, int lde, const float *es,
+                      const float *et, float *dx, int lddx, double *partial, sg4d_stream_t stream);
+/* dW (m x k, row stride lddw) = dY^T * act(x);  act(x) = x (xs NULL) or relu(x .* xs + xt);  computed as 128 x 128 blocks in
+ * one launch;  partial: sg4d_dense_wgrad_partial_floats(rows, m, k) floats of scratch. */
+long long sg4d_dense_wgrad_partial_floats(long long rows, int m, int k);
+int sg4d_dense_bwd_dw(long long rows, int m, int lda, int k, int mode, const float *a, const float *a2, const float *p1,
+                      const float *q1, const float *u1, const float *x, int ldx, const float *xs, const float *xt,
+                      float *partial, float *dw, int lddw, sg4d_stream_t stream);
+/* dW2 (m x n) = dY2^T * relu(y1 .* s1 + t1) for wide pooled layers (dY2 as in sg4d_pool_bwd_da; m = C2, n = C1);
+ * partial: sg4d_dense_wgrad_partial_floats(rows, m, n).  sg4d_pool_bwd_da itself accepts n = C1 that is a multiple of 128
+ * (column panels, wimg_t = the dense image of W2^T, partial = sg4d_dense_partial_doubles(rows, n)) and k = C2 <= 1280. */
+int sg4d_dense_pool_bwd_dw(long long rows, int m, int n, int group, const float *y2, const float *a2, const float *b2,
+                           const float *dsel, const uint8_t *garg, const float *y1, const float *s1, const float *t1,
+                           float *partial, float *dw, sg4d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,8 +5,41 @@ and the full-size GPU parity tests.  Follows the reference op sequence: grouping
 sg4d's forward pass (and checked to differ from the fp64 choice only where the value is within rounding of a tie /
 of zero): with them fixed, outputs and gradients are smooth in the inputs and can be compared at 1e-4 with no outliers."""
 import torch
+import torch.nn as nn
+import torch.nn.functional as F
 
 EPS = 1e-5
+
+
+def _batch_norm_rows(bn, x):
+    """nn.BatchNorm2d.forward on a (rows, C) matrix: statistics over rows == over (B, H, W)."""
+    use_batch_stats = bn.training or not bn.track_running_stats
+    momentum = 0.0 if bn.momentum is None else bn.momentum
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if bn.momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    return F.batch_norm(x, bn.running_mean if (not bn.training or bn.track_running_stats) else None,
+                        bn.running_var if (not bn.training or bn.track_running_stats) else None,
+                        bn.weight, bn.bias, use_batch_stats, momentum, bn.eps)
+
+
+def shared_mlp_rows(mlp: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
+    """Apply a ``build_shared_mlp`` stack to x (rows, K_padded); extra zero columns are ignored."""
+    for layer in mlp:
+        if isinstance(layer, nn.Conv2d):
+            w = layer.weight.view(layer.out_channels, layer.in_channels)
+            if x.shape[1] != w.shape[1]:
+                w = F.pad(w, (0, x.shape[1] - w.shape[1]))
+            x = F.linear(x, w, layer.bias)
+        elif isinstance(layer, nn.BatchNorm2d):
+            x = _batch_norm_rows(layer, x)
+        elif isinstance(layer, nn.ReLU):
+            x = F.relu(x, inplace=True)
+        else:
+            raise TypeError(f"unexpected layer in shared MLP: {type(layer).__name__}")
+    return x
+
 
 
 def grouped_fp64(pts, feats, foff, c, centers, idx):

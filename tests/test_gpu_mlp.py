@@ -72,7 +72,7 @@ def _mlp(cin, c1, c2, seed):
 def test_fused_shared_mlp_matches_unfused_modules(cuda, cin, kp, c1, c2, group, groups, dx):
     """fused tensor-core forward+backward vs the same nn.Sequential evaluated with stock fp32 PyTorch ops"""
     from sg4d import mlp
-    from sg4d.pointnet2_ops.pointnet2_modules import shared_mlp_rows
+    from sa_ref import shared_mlp_rows
     m_f = _mlp(cin, c1, c2, 3).to(cuda).train()
     m_r = copy.deepcopy(m_f)
     assert mlp.supported(m_f, kp, group)
