@@ -53,8 +53,23 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run the two encoders on one stream")
-    ap.add_argument("--cpu-clouds", type=int, default=13, help="clouds in the CPU sample (13 = 1/6 scene)")
-    return ap.parse_args()
+    ap.add_argument("--cpu-clouds", type=int, default=78, help="clouds in the CPU legs (default: one full scene; fewer = a scaled sample)")
+    ap.add_argument("--config", type=int, default=3, choices=[1, 2, 3, 4, 5],
+                    help="BASELINE.json configs[config-1]: 1 = 1 scene x 2048 pts forward only; 2 = 8 scenes, encoders only, "
+                         "fwd+bwd; 3 = 8 scenes, full pipeline (default, the headline); 4 = 32 scenes + image branch; "
+                         "5 = 32 scenes per GPU (256 at 8 GPUs)")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's own code on the GPU")
+    a = ap.parse_args()
+    a.forward_only, a.encoders_only, a.image = False, False, False
+    if a.config == 1:
+        a.scenes_per_gpu, a.points, a.n_obj, a.forward_only = 1, 2048, 4, True
+    elif a.config == 2:
+        a.encoders_only = True
+    elif a.config == 4:
+        a.scenes_per_gpu, a.image = 32, True
+    elif a.config == 5:
+        a.scenes_per_gpu = 32
+    return a
 
 
 def load_peaks():
@@ -116,13 +131,18 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------- CPU arm
 
 def cpu_sample_batch(args, n_clouds):
-    """A bounded sample of the workload for the CPU legs: n_clouds clouds of a scene in the scene's own
-    object:edge proportion (12:66), GNN run on as many edges as there are edge clouds."""
+    """The workload of the CPU legs: ONE full scene of the benchmark shape (12 + 66 clouds, its real edge list) when
+    n_clouds covers it; otherwise a bounded sample -- n_clouds clouds in the scene's own object:edge proportion, the
+    GNN run on as many (random) edges as there are edge clouds -- whose scenes/s is scaled by the cloud count."""
     from sg4d import synthetic
-    n_obj = max(2, round(n_clouds * 12 / CLOUDS_PER_SCENE))   # BatchNorm1d over the nodes / edges needs >= 2 rows
+    pr = args.points_rel or args.points
+    n_edge = args.n_obj * (args.n_obj - 1) // (2 if args.pairs == "unordered" else 1)
+    if n_clouds >= args.n_obj + n_edge:
+        return synthetic.make_scene(4321, n_obj=args.n_obj, n_points_obj=args.points, n_points_rel=pr, pairs=args.pairs), \
+            args.n_obj + n_edge, "one full scene"
+    n_obj = max(2, round(n_clouds * args.n_obj / (args.n_obj + n_edge)))   # BatchNorm1d over the nodes / edges needs >= 2 rows
     n_rel = max(2, n_clouds - n_obj)
     gen = torch.Generator().manual_seed(4321)
-    pr = args.points_rel or args.points
     obj = torch.stack([synthetic.make_cloud(gen, args.points, 6) for _ in range(n_obj)])
     rel = torch.stack([synthetic.make_cloud(gen, pr, 7) for _ in range(n_rel)])
     ei = torch.stack([torch.randint(0, n_obj, (n_rel,), generator=gen), torch.randint(0, n_obj, (n_rel,), generator=gen)])
@@ -131,18 +151,27 @@ def cpu_sample_batch(args, n_clouds):
     one_hot[:, 6] = 1
     return {"obj_points": obj.permute(0, 2, 1), "rel_points": rel.permute(0, 2, 1), "edge_indices": ei,
             "relation_objects_one_hot": one_hot, "gt_class": torch.randint(0, 12, (n_obj,), generator=gen),
-            "gt_rels": torch.randint(0, 15, (n_rel,), generator=gen)}, n_obj + n_rel
+            "gt_rels": torch.randint(0, 15, (n_rel,), generator=gen)}, n_obj + n_rel, \
+        f"SAMPLE of {n_obj + n_rel} of a scene's {args.n_obj + n_edge} clouds with random edges, scaled by cloud count"
 
 
-def cpu_step(sd, batch):
+def cpu_step(sd, batch, args):
     from oracle import model_ref
     for v in sd.values():
         if v.requires_grad:
             v.grad = None
-    outs = model_ref.forward(sd, batch, training=True, dropout=True)
-    loss = model_ref.loss_fn(outs[0], outs[1], batch, torch.ones(12), torch.ones(15), 1e-6)
+    if args.forward_only:
+        with torch.no_grad():
+            outs = model_ref.forward(sd, batch, training=True, dropout=True)
+            return float(model_ref.loss_fn(outs[0], outs[1], batch, torch.ones(12), torch.ones(15), 1e-6))
+    if args.encoders_only:
+        loss = model_ref.encoder(sd, "obj_encoder", batch["obj_points"], True).sum() + \
+            model_ref.encoder(sd, "rel_encoder", batch["rel_points"], True).sum()
+    else:
+        outs = model_ref.forward(sd, batch, training=True, dropout=True)
+        loss = model_ref.loss_fn(outs[0], outs[1], batch, torch.ones(12), torch.ones(15), 1e-6)
     loss.backward()
-    return float(loss)
+    return float(loss.detach())
 
 
 def run_cpu(args, steps, warmup, budget_s):
@@ -153,26 +182,28 @@ def run_cpu(args, steps, warmup, budget_s):
     torch.set_num_threads(cores)
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     sd = model_ref.clone_state(weights.synth_state_dict(seed=0))
-    n_clouds = args.cpu_clouds
+    n_edge = args.n_obj * (args.n_obj - 1) // (2 if args.pairs == "unordered" else 1)
+    scene_clouds = args.n_obj + n_edge
+    n_clouds = min(args.cpu_clouds, scene_clouds)
     while True:
-        batch, used = cpu_sample_batch(args, n_clouds)
+        batch, used, what = cpu_sample_batch(args, n_clouds)
         t0 = time.perf_counter()
-        cpu_step(sd, batch)
+        cpu_step(sd, batch, args)
         t1 = time.perf_counter() - t0
         if t1 * (steps + warmup) <= budget_s or n_clouds <= 2:
             break
         n_clouds = max(2, int(n_clouds * budget_s / (t1 * (steps + warmup))))
     for _ in range(max(0, warmup - 1)):
-        cpu_step(sd, batch)
+        cpu_step(sd, batch, args)
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        cpu_step(sd, batch)
+        cpu_step(sd, batch, args)
         times.append(time.perf_counter() - t0)
     per_step = sum(times) / len(times)
-    scenes = used / CLOUDS_PER_SCENE
+    scenes = used / scene_clouds
     desc = {"kind": "port", "cores": cores, "unit": "scenes/s",
-            "sample": f"{used} of a scene's {CLOUDS_PER_SCENE} clouds ({args.points} pts each), fwd+loss+bwd, "
+            "sample": f"{what} ({args.points} pts per cloud), {'forward' if args.forward_only else 'fwd+loss+bwd'}, "
                       f"{steps} timed steps of {per_step:.2f} s; oracle/pn2_oracle.c (OpenMP over clouds) + "
                       f"oracle/model_ref.py (torch CPU, {cores} threads)"}
     return scenes / per_step, per_step * 1e3, desc
@@ -181,8 +212,12 @@ def run_cpu(args, steps, warmup, budget_s):
 def workload_name(args):
     pr = args.points_rel or args.points
     n_edge = args.n_obj * (args.n_obj - 1) // (2 if args.pairs == "unordered" else 1)
-    return (f"BASELINE configs[2]: {args.scenes_per_gpu} scenes/GPU x ({args.n_obj} obj x {args.points} pts + "
-            f"{n_edge} edges x {pr} pts), PointNet++ MSG encoders + TripletGCN + heads, fwd+loss+bwd, fp32")
+    what = {1: "full pipeline, forward only", 2: "PointNet++ MSG encoders only (upstream gradient = ones), fwd+bwd",
+            3: "PointNet++ MSG encoders + TripletGCN + heads, fwd+loss+bwd",
+            4: "full pipeline + image-feature concat branch, fwd+loss+bwd (fp32: the bf16 path is not built)",
+            5: "full pipeline, fwd+loss+bwd, scene-sharded data parallel"}[args.config]
+    return (f"BASELINE configs[{args.config - 1}]: {args.scenes_per_gpu} scenes/GPU x ({args.n_obj} obj x {args.points} pts + "
+            f"{n_edge} edges x {pr} pts), {what}, fp32")
 
 
 def main_reference(args):
@@ -194,8 +229,9 @@ def main_reference(args):
     line = {"impl": "reference", "metric": "scenes/sec fwd+bwd", "value": value, "unit": "scenes/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "note": "reference has no CPU path for its custom ops; "
-                       "this is the oracle port of its arithmetic on the host cores, rank 0 only"},
+            "config": {"workload": workload_name(args), "cpu_sample": desc["sample"],
+                       "note": "reference has no CPU path for its custom ops; this is the oracle port of its arithmetic on "
+                               "the host cores, rank 0 only; scenes/s of the CPU sample (see cpu_sample)"},
             "cpu_baseline": desc,
             "e2e": {"value": value, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -221,6 +257,8 @@ def main_sg4d(args):
     torch.backends.cuda.matmul.allow_tf32 = False
 
     cfg = model_config()
+    if args.image:
+        cfg["IMAGE_INPUT"] = "full"
     torch.manual_seed(0)
     names = [f"rel{i}" for i in range(14)] + ["none"]
     model = SGPNModelWrapper(cfg, 12, 15, torch.ones(12), torch.ones(15), names).to(dev).train()
@@ -230,7 +268,7 @@ def main_sg4d(args):
     S = args.scenes_per_gpu
     pr = args.points_rel or args.points
     host = synthetic.make_batch(rank * S, S, n_obj=args.n_obj, n_points_obj=args.points, n_points_rel=pr,
-                                pairs=args.pairs)
+                                pairs=args.pairs, image=args.image)
     tensor_keys = [k for k, v in host.items() if torch.is_tensor(v)]
     pinned = {}
     for k in tensor_keys:
@@ -244,8 +282,15 @@ def main_sg4d(args):
     resident = synthetic.to_device(pinned, dev)
 
     def step(batch):
+        if args.forward_only:                       # config 1: forward + loss, no gradients
+            with torch.no_grad():
+                return model.training_step(batch)
         bucket.zero()
-        loss = model.training_step(batch)
+        if args.encoders_only:                      # config 2: both encoders, upstream gradient of ones, no GNN / heads
+            obj_f, rel_f = model._encode(batch)
+            loss = obj_f.sum() + rel_f.sum()
+        else:
+            loss = model.training_step(batch)
         loss.backward()
         bucket.all_reduce_mean()
         return loss
@@ -258,6 +303,7 @@ def main_sg4d(args):
     for _ in range(args.warmup):
         step(resident)
     barrier()
+    torch.cuda.reset_peak_memory_stats(dev)
 
     # ---- timed region 1: inputs resident in HBM (working set of 1.4 GB/step >> 126 MB L2)
     launches0 = _lib.LAUNCH_COUNT
@@ -271,6 +317,7 @@ def main_sg4d(args):
         barrier()
     total_ms = ev[0].elapsed_time(ev[-1])
     launches = _lib.LAUNCH_COUNT - launches0
+    peak_mem_gb = torch.cuda.max_memory_allocated(dev) / 1e9
 
     # ---- kernel table: the same steps once more with a CUDA-event pair around every C-ABI call (on the launching
     #      stream).  The encoders share one stream here so that a call's duration is its own, not that of whatever
@@ -330,58 +377,107 @@ def main_sg4d(args):
 
     # ---- per-kernel table and the roofline of the dominant own kernel
     peak, peak_src = load_peaks()
+    pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    tpeak = pk.get("bf16_tflops_sustained", 1384.6)
     kernels = []
     for (name, key), ms in per_call.items():
         kernels.append({"call": name, "args": list(key), "launches_per_step": len(ms) / args.steps,
                         "avg_ms": sum(ms) / len(ms), "ms_per_step": sum(ms) / args.steps})
     kernels.sort(key=lambda k: -k["ms_per_step"])
     own_ms = sum(k["ms_per_step"] for k in kernels)
-    roof = None
-    for k in kernels:
-        nm, a = k["call"], k["args"]
-        bts = None
+
+    # Algorithmic bytes (inputs read once + outputs written once; a gathered cloud counts once per launch) and
+    # algorithmic FLOPs (2 x MACs of the layer the call evaluates; recomputation is NOT counted) per call.
+    # args = the call's small integer arguments in order (see include/sg4d.h).
+    def model_of(nm, a):
         if nm in ("sg4d_fps_rows", "sg4d_fps_indexed"):
-            bts = a[0] * (12 * a[1] + 16 * a[2])                          # read xyz once, write idx + picked xyz
-        elif nm == "sg4d_spatial_index_build":
-            bts = a[0] * a[1] * (12 + 20)                                 # read xyz, write the sorted {x,y,z,k} + t
-        elif nm == "sg4d_group_rows":
+            return a[0] * (12 * a[1] + 16 * a[2]), 0
+        if nm == "sg4d_spatial_index_build":
+            return a[0] * a[1] * (12 + 20), 0
+        if nm == "sg4d_group_rows":
             b_, n_, m_, ns_, c_ = a[:5]
-            bts = b_ * (4 * m_ * ns_ + 4 * (3 + c_) * m_ * ns_ + 12 * m_) + b_ * min(n_, m_ * ns_) * 4 * (3 + c_)
-        elif nm == "sg4d_group_rows_grad":
+            return b_ * (4 * m_ * ns_ + 4 * (3 + c_) * m_ * ns_ + 12 * m_) + b_ * min(n_, m_ * ns_) * 4 * (3 + c_), 0
+        if nm == "sg4d_group_rows_grad":
             b_, n_, m_, ns_, c_ = a[:5]
-            bts = b_ * (4 * c_ * m_ * ns_ + 4 * m_ * ns_ + 4 * c_ * n_)
-        elif nm == "sg4d_linear_fwd":            # (rows, k, lda, n, group): read the operand rows, write the pre-activations
-            bts = a[0] * 4 * (a[1] + a[3])
-        elif nm == "sg4d_pool_bwd_da":           # (rows, C2, C1, group): read y2, y1; write dz1
-            bts = a[0] * 4 * (a[1] + 2 * a[2])
-        elif nm == "sg4d_pool_bwd_dw":           # (rows, C2, C1, group): read y2, y1
-            bts = a[0] * 4 * (a[1] + a[2])
-        elif nm == "sg4d_inner_bwd_dx":          # (rows, C1, n): read y1, dz1; write n columns of dX
-            bts = a[0] * 4 * (2 * a[1] + a[2])
-        elif nm == "sg4d_inner_bwd_dw":          # (rows, C1, k, ldx): read y1, dz1, x
-            bts = a[0] * 4 * (2 * a[1] + a[2])
-        elif nm in ("sg4d_ball_query_rows", "sg4d_ball_query_rows_indexed"):
+            return b_ * (4 * c_ * m_ * ns_ + 4 * m_ * ns_ + 4 * c_ * n_), 0
+        if nm in ("sg4d_ball_query_rows", "sg4d_ball_query_rows_indexed"):
             b_, n_, m_ = a[:3]
-            bts = b_ * (12 * n_ + 12 * m_)                                # + 4*m*sum(ns) (small)
+            return b_ * (12 * n_ + 12 * m_), 0
+        if nm == "sg4d_linear_fwd":              # (rows, k, lda, n, group)
+            return a[0] * 4 * (a[1] + a[3]), 2 * a[0] * a[1] * a[3]
+        if nm == "sg4d_pool_bwd_da":             # (rows, C2, C1, group): read y2, y1; write dz1
+            return a[0] * 4 * (a[1] + 2 * a[2]), 2 * a[0] * a[1] * a[2]
+        if nm in ("sg4d_pool_bwd_dw", "sg4d_dense_pool_bwd_dw"):
+            return a[0] * 4 * (a[1] + a[2]), 2 * a[0] * a[1] * a[2]
+        if nm == "sg4d_inner_bwd_dx":            # (rows, C1, n, lddx, col0)
+            return a[0] * 4 * (2 * a[1] + a[2]), 2 * a[0] * a[1] * a[2]
+        if nm == "sg4d_inner_bwd_dw":            # (rows, C1, k, ldx)
+            return a[0] * 4 * (2 * a[1] + a[2]), 2 * a[0] * a[1] * a[2]
+        if nm in ("sg4d_sa1_fwd", "sg4d_sa1_bwd_da", "sg4d_sa1_bwd_dw2", "sg4d_sa_moments"):
+            rows, n_, m_, ns_, ps_, fs_ = a[:6]       # then [foff,] c, n2 (zero-valued arguments are not recorded)
+            n2 = a[-1] if nm != "sg4d_sa_moments" else 0
+            clouds = rows // (m_ * ns_)
+            cloud_bytes = clouds * n_ * ps_ * 4       # the gathered cloud, once
+            pooled = (rows // ns_) * n2 * 5
+            if nm == "sg4d_sa_moments":
+                return rows * 4 + cloud_bytes, 0
+            fl = 2 * rows * 64 * n2 + (2 * rows * 8 * 64 if nm != "sg4d_sa1_bwd_dw2" else 0)
+            return rows * (4 + 4 * n2) + cloud_bytes + pooled, fl
+        if nm == "sg4d_linear_fwd_grouped":      # (rows, n, m, ns, pstride, fstride, c, nout)
+            rows, n_, m_, ns_, ps_, fs_ = a[:6]
+            c_, nout = a[-2], a[-1]
+            clouds = rows // (m_ * ns_)
+            return rows * (4 + 4 * nout) + clouds * n_ * (fs_ + 3) * 4, 2 * rows * (c_ + 3) * nout
+        if nm == "sg4d_inner_bwd_dw_grouped":    # (..., c, mout, lddw)
+            rows, n_, m_, ns_, ps_, fs_ = a[:6]
+            c_, mout = a[-3], a[-2]
+            clouds = rows // (m_ * ns_)
+            return rows * (4 + 8 * mout) + clouds * n_ * (fs_ + 3) * 4, 2 * rows * (c_ + 3) * mout
+        if nm == "sg4d_dense_fwd":               # (rows, k, lda, n, ldy[, group])
+            return a[0] * 4 * (a[1] + a[3]), 2 * a[0] * a[1] * a[3]
+        if nm == "sg4d_dense_bwd_dx":            # (rows, kk, lda, nout, mode?, ...)
+            return a[0] * 4 * (2 * a[1] + a[3]), 2 * a[0] * a[1] * a[3]
+        if nm == "sg4d_dense_bwd_dw":            # (rows, m, lda, k, ...)
+            return a[0] * 4 * (2 * a[1] + a[3]), 2 * a[0] * a[1] * a[3]
+        return None, 0
+
+    for k in kernels:
+        try:
+            bts, fl = model_of(k["call"], k["args"])
+        except (IndexError, ZeroDivisionError):
+            bts, fl = None, 0
         if bts:
             k["algorithmic_bytes"] = bts
             k["achieved_gbs"] = bts / (k["avg_ms"] * 1e-3) / 1e9
             k["hbm_frac"] = k["achieved_gbs"] / peak
+        if fl:
+            k["algorithmic_flops"] = fl
     # ---- roofline of the DOMINANT KERNEL: calls are grouped by the kernel that does their work; achieved =
     #      algorithmic bytes of all its launches / their summed duration (= bytes per launch / average launch duration)
-    family = {"sg4d_linear_fwd": "row_gemm_kernel", "sg4d_pool_bwd_da": "row_gemm_kernel", "sg4d_inner_bwd_dx": "row_gemm_kernel",
-              "sg4d_pool_bwd_dw": "wgrad_kernel", "sg4d_inner_bwd_dw": "wgrad_kernel",
-              "sg4d_fps_indexed": "fps_indexed_kernel", "sg4d_fps_rows": "fps_onchip_kernel",
-              "sg4d_ball_query_rows_indexed": "ball_query_kernel+ball_query_indexed_kernel",
-              "sg4d_ball_query_rows": "ball_query_kernel", "sg4d_group_rows": "group_rows_kernel",
-              "sg4d_group_rows_grad": "group_rows_grad_kernel", "sg4d_spatial_index_build": "spatial_build_kernel"}
+    row_calls = ("sg4d_linear_fwd", "sg4d_pool_bwd_da", "sg4d_inner_bwd_dx", "sg4d_sa1_fwd", "sg4d_sa1_bwd_da",
+                 "sg4d_linear_fwd_grouped", "sg4d_dense_fwd", "sg4d_dense_bwd_dx")
+    wg_calls = ("sg4d_pool_bwd_dw", "sg4d_inner_bwd_dw", "sg4d_sa1_bwd_dw2", "sg4d_inner_bwd_dw_grouped", "sg4d_dense_bwd_dw",
+                "sg4d_dense_pool_bwd_dw")
+    family = {c: "row_gemm_kernel" for c in row_calls}
+    family.update({c: "wgrad_kernel" for c in wg_calls})
+    family.update({"sg4d_fps_indexed": "fps_indexed_kernel", "sg4d_fps_rows": "fps_onchip_kernel",
+                   "sg4d_ball_query_rows_indexed": "ball_query_kernel+ball_query_indexed_kernel",
+                   "sg4d_ball_query_rows": "ball_query_kernel", "sg4d_group_rows": "group_rows_kernel",
+                   "sg4d_group_rows_grad": "group_rows_grad_kernel", "sg4d_spatial_index_build": "spatial_build_kernel"})
     fam = {}
     for k in kernels:
-        f = fam.setdefault(family.get(k["call"], k["call"]), {"ms": 0.0, "bytes": 0.0, "launches": 0.0, "calls": set()})
+        f = fam.setdefault(family.get(k["call"], k["call"]), {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "launches": 0.0, "calls": set()})
         f["ms"] += k["ms_per_step"]
         f["bytes"] += k.get("algorithmic_bytes", 0) * k["launches_per_step"]
+        f["flops"] += k.get("algorithmic_flops", 0) * k["launches_per_step"]
         f["launches"] += k["launches_per_step"]
         f["calls"].add(k["call"])
+
+    traffic_file = None
+    for cand in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        if os.path.exists(os.path.join(ROOT, "profiles", cand)):
+            traffic_file = cand
+            break
 
     def fam_roof(name, f):
         ach = f["bytes"] / (f["ms"] * 1e-3) / 1e9 if f["ms"] > 0 and f["bytes"] > 0 else None
@@ -389,29 +485,80 @@ def main_sg4d(args):
              "avg_launch_ms": f["ms"] / max(f["launches"], 1e-9), "algorithmic_bytes_per_launch": f["bytes"] / max(f["launches"], 1e-9),
              "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if ach else None, "traffic": None,
              "peak_source": peak_src, "share_of_step": f["ms"] / table_ms_per_step}
-        tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-        if os.path.exists(tp):   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
-            t = json.load(open(tp)).get("kernels", {}).get(name.split("+")[0])
+        if traffic_file:   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
+            t = json.load(open(os.path.join(ROOT, "profiles", traffic_file))).get("kernels", {}).get(name.split("+")[0])
             if t and t.get("launches"):
                 r["traffic"] = t["dram_bytes"] / t["launches"]
-                r["traffic_source"] = "profiles/r01_ncu_traffic.json (ncu, same workload; average per launch)"
+                r["traffic_source"] = f"profiles/{traffic_file} (ncu, same workload; average per launch)"
         return r
 
+    roof = None
     if fam:
         top_name = max(fam, key=lambda n: fam[n]["ms"])
         roof = fam_roof(top_name, fam[top_name])
         roof["others"] = {n: {"ms_per_step": f["ms"], "hbm_frac": (f["bytes"] / (f["ms"] * 1e-3) / 1e9 / peak) if f["bytes"] else None}
                           for n, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]) if n != top_name}
-        # the pair BASELINE.json's north star singles out: ball query + group (SA1 and SA2 together)
-        bqg = {"ms": 0.0, "bytes": 0.0, "launches": 0.0, "calls": set()}
-        for n in ("ball_query_kernel+ball_query_indexed_kernel", "ball_query_kernel", "group_rows_kernel"):
-            if n in fam:
-                for key in ("ms", "bytes", "launches"):
-                    bqg[key] += fam[n][key]
-                bqg["calls"] |= fam[n]["calls"]
-        if bqg["ms"] > 0:
-            roof["ball_query_plus_group"] = {k2: v for k2, v in fam_roof("ball query + group", bqg).items()
-                                             if k2 in ("achieved", "frac", "unit", "share_of_step", "avg_launch_ms", "calls")}
+        # the shared MLP against the TENSOR roofline: algorithmic FLOPs of every layer evaluation of the
+        # step / the summed duration of the two tensor-core kernels / the sustained dense bf16 peak (tf32 runs at half
+        # of it, and 3xTF32 issues three products per algorithmic one: both are kept OUT of the numerator on purpose)
+        mlp_ms = sum(fam[n]["ms"] for n in ("row_gemm_kernel", "wgrad_kernel") if n in fam)
+        mlp_fl = sum(fam[n]["flops"] for n in ("row_gemm_kernel", "wgrad_kernel") if n in fam)
+        if mlp_ms > 0:
+            roof["mlp_tensor"] = {"bound": "tensor", "algorithmic_flops_per_step": mlp_fl, "ms_per_step": mlp_ms,
+                                  "achieved": mlp_fl / (mlp_ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                                  "frac": mlp_fl / (mlp_ms * 1e-3) / 1e12 / tpeak,
+                                  "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if pk else "fallback"}
+        # the pair BASELINE.json's north star singles out: ball query + group.  The group is fused into the operand
+        # stagers of the MLP kernels (the grouped tensor is never written), so the pair's time is the ball-query
+        # kernels' and its bytes are the op-level contract of SURVEY.md 8(d): query (12n + 12m + 4 m ns) + grouped
+        # output 4 (3 + C) m ns per scale and cloud.
+        bq_ms, bq_bytes, calls = 0.0, 0.0, set()
+        for k in kernels:
+            if k["call"] in ("sg4d_ball_query_rows", "sg4d_ball_query_rows_indexed"):
+                bq_ms += k["ms_per_step"]
+                bq_bytes += k.get("algorithmic_bytes", 0) * k["launches_per_step"]
+                calls.add(k["call"])
+            if k["call"] in ("sg4d_sa1_fwd", "sg4d_linear_fwd_grouped", "sg4d_group_rows"):
+                a = k["args"]
+                width = 8 if k["call"] == "sg4d_sa1_fwd" else (a[-2] + 3 if k["call"] == "sg4d_linear_fwd_grouped" else a[4] + 3)
+                rows_ = a[0] if k["call"] != "sg4d_group_rows" else a[0] * a[2] * a[3]
+                bq_bytes += rows_ * (4 + 4 * width) * k["launches_per_step"]
+                if k["call"] == "sg4d_group_rows":
+                    bq_ms += k["ms_per_step"]
+                calls.add(k["call"])
+        if bq_ms > 0:
+            roof["ball_query_plus_group"] = {"achieved": bq_bytes / (bq_ms * 1e-3) / 1e9, "unit": "GB/s",
+                                             "frac": bq_bytes / (bq_ms * 1e-3) / 1e9 / peak, "ms_per_step": bq_ms,
+                                             "share_of_step": bq_ms / table_ms_per_step, "calls": sorted(calls),
+                                             "note": "time = the ball-query launches (+ group_rows where a scale still "
+                                                     "materialises rows); bytes = query + grouped-output contract"}
+
+    # ---- the REFERENCE ITSELF on this GPU: its own Python over its own kernels (oracle/ref_gpu.py), batch_size = 1 like
+    #      its main.py, same synthetic scenes; fp32 with TF32 off, and fp16 autocast (its native `precision=16`)
+    gpu_ref = None
+    if world == 1 and not args.no_gpu_reference and not args.encoders_only:
+        try:
+            from oracle import ref_gpu
+            if ref_gpu.available():
+                del resident
+                torch.cuda.empty_cache()
+                rm = ref_gpu.build_model(dev)
+                nsc = 1 if args.forward_only else 2
+                scenes = [synthetic.to_device(synthetic.make_scene(900 + i, n_obj=args.n_obj, n_points_obj=args.points,
+                                                                   n_points_rel=pr, pairs=args.pairs), dev) for i in range(nsc)]
+                for sc in scenes:
+                    sc["take_idx"] = 0
+                v32, ms32, wall32 = ref_gpu.time_scenes(rm, scenes, reps=2)
+                v16, ms16, wall16 = ref_gpu.time_scenes(rm, scenes, reps=2, autocast=True)
+                gpu_ref = {"kind": "reference", "what": "the reference's own SGPNModelWrapper (Python, unmodified) over its own CUDA "
+                           "kernels compiled for sm_100a, one scene per forward+backward (main.py's batch_size=1), same GPU",
+                           "fp32_tf32_off": {"value": v32, "unit": "scenes/s", "ms_per_scene": ms32},
+                           "fp16_autocast": {"value": v16, "unit": "scenes/s", "ms_per_scene": ms16},
+                           "scenes_timed": 2 * nsc, "sg4d_over_reference_fp32": value / v32, "sg4d_over_reference_fp16": value / v16}
+            else:
+                gpu_ref = {"unavailable": "oracle/_ref/pn2_ref_ext.so or the staged reference Python is missing on this box"}
+        except Exception as e:   # measurement infrastructure must never take the bench line down
+            gpu_ref = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -423,9 +570,11 @@ def main_sg4d(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "scenes_per_gpu": S, "global_scenes": S * world,
                        "parallelism": f"dp{world} (scene-sharded, one grad all-reduce)",
-                       "l2": f"inputs are {h2d_bytes / 1e6:.0f} MB per step per GPU (> 126 MB L2), no flush needed"},
+                       "l2": f"inputs are {h2d_bytes / 1e6:.0f} MB per step per GPU (> 126 MB L2), no flush needed",
+                       "peak_memory_gb": round(peak_mem_gb, 2),
+                       "cpu_sample": cpu["sample"] if cpu else None},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "cpu_baseline": cpu, "gpu_reference": gpu_ref,
             "kernel_table": {"ms_per_step": table_ms_per_step, "own_kernel_ms_per_step": own_ms,
                              "note": "second pass of the same steps, one stream, CUDA events around every C-ABI call"},
             "kernels": kernels[:48]}

@@ -38,6 +38,32 @@ def build(verbose=False):
     return so_path()
 
 
+REF_PKG = "/root/reference/scene_graph_prediction"
+STAGE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "reference")
+
+
+def stage_reference_python():
+    """Container-only: "installs" the reference's Python (the *.py / *.json files of scene_graph_prediction/, 236 KB,
+    unmodified, same tree) into the git-ignored baseline/_ref/reference/ so that the reference arm can run the
+    reference's OWN model code on the GPU box, where /root/reference does not exist (the reference has no setup.py
+    for this package; `pip install /root/reference` has nothing to install).  Nothing here enters the repository."""
+    import shutil
+    if not os.path.isdir(REF_PKG):
+        return None
+    dst_root = os.path.join(STAGE, "scene_graph_prediction")
+    for root, dirs, files in os.walk(REF_PKG):
+        for d in dirs:      # keep the package tree (some packages are bare directories = namespace packages)
+            os.makedirs(os.path.join(dst_root, os.path.relpath(os.path.join(root, d), REF_PKG)), exist_ok=True)
+        for f in files:
+            if f.endswith((".py", ".json")):
+                src = os.path.join(root, f)
+                dst = os.path.join(dst_root, os.path.relpath(src, REF_PKG))
+                os.makedirs(os.path.dirname(dst), exist_ok=True)
+                if not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
+                    shutil.copyfile(src, dst)
+    return STAGE
+
+
 def load_module():
     """Import the prebuilt extension (GPU box or container); None when it was never built."""
     p = so_path()

@@ -1,5 +1,6 @@
-"""oracle/ref_harness.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Works only where
-``/root/reference`` exists (the build container); nothing that runs on the GPU box imports it.
+"""oracle/ref_harness.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Works where ``/root/reference`` is mounted
+(the build container) or where its Python has been staged under the git-ignored ``baseline/_ref/reference``
+(oracle/build_ref_ext.py:stage_reference_python; that copy travels to the GPU box for bench.py's reference arm).
 
 Imports the reference's OWN Python for the hot path -- ``pointnet2_ops.pointnet2_utils`` /
 ``pointnet2_modules`` (OPS/), ``PointNet2ClassificationMSG`` (PN2/models/pointnet2_msg_cls.py),
@@ -27,7 +28,9 @@ import types
 
 import torch
 
-REF_ROOT = "/root/reference"
+# the mounted reference (build container) or its staged, git-ignored copy (GPU box; oracle/build_ref_ext.py)
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "reference")
+REF_ROOT = "/root/reference" if os.path.isdir("/root/reference/scene_graph_prediction") else _STAGED
 OPS_LIB = os.path.join(REF_ROOT, "scene_graph_prediction/pointnet2_dir/pointnet2_ops_lib")
 
 
@@ -67,7 +70,7 @@ def install(ext_module):
     """Seed sys.modules; ``ext_module`` becomes ``pointnet2_ops._ext``.  Idempotent per process
     (the reference binds _ext at import time, so one process = one ext)."""
     if not available():
-        raise RuntimeError("/root/reference is not present (this harness is container-only)")
+        raise RuntimeError("the reference's Python is neither mounted at /root/reference nor staged under baseline/_ref")
     if "pointnet2_ops._ext" in sys.modules and sys.modules["pointnet2_ops._ext"] is not ext_module:
         raise RuntimeError("reference already imported with another _ext in this process")
     _mod("pytorch_lightning", LightningModule=torch.nn.Module, seed_everything=lambda s: None)
