@@ -14,7 +14,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libsg4d.so")
+SO_PATH = os.environ.get("SG4D_LIBRARY") or os.path.join(_HERE, "libsg4d.so")     # SG4D_LIBRARY: a developer (debug) build
 
 _i, _i64, _f, _p = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 

@@ -33,7 +33,14 @@ def _stale(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, debug=False):
+    """debug=True: a separate libsg4d_dbg.so with -DSG4D_DEBUG (ablation switches + timeline tracing of the MLP kernels;
+    developer tools select it with SG4D_LIBRARY=<path>)."""
+    global OBJ, SO
+    flags = list(FLAGS)
+    if debug:
+        OBJ, SO = os.path.join(HERE, "build_dbg"), os.path.join(HERE, "libsg4d_dbg.so")
+        flags.append("-DSG4D_DEBUG")
     os.makedirs(OBJ, exist_ok=True)
     hdrs = _deps()
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
@@ -41,7 +48,7 @@ def build(force=False, verbose=False):
     for s in srcs:
         src, obj = os.path.join(CSRC, s), os.path.join(OBJ, s[:-3] + ".o")
         if force or _stale(obj, [src] + hdrs):
-            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = [NVCC] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             jobs.append(cmd)
 
     def run(cmd):
@@ -61,4 +68,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, debug="--debug" in sys.argv))

@@ -251,8 +251,17 @@ struct RowSmem {
 // PT = producer threads: 256, or 512 for layers with many k-blocks per tile (K >= 128), which are producer-bound
 #ifdef SG4D_DEBUG
 #define SG4D_DBG(x) (x)
+// timeline tracing of CTA 0 (tools/trace_mlp.py): one clock64() stamp per (role, event, index)
+__device__ unsigned long long *g_trace = nullptr;
+#define SG4D_TRACE_INIT() unsigned long long *trc = (blockIdx.x == 0 && blockIdx.y == 0) ? g_trace : nullptr
+#define SG4D_TRACE(cond, slot)                                                 \
+    do {                                                                       \
+        if (trc && (cond) && (slot) < 8192) trc[(slot)] = clock64();           \
+    } while (0)
 #else
 #define SG4D_DBG(x) 0
+#define SG4D_TRACE_INIT() do { } while (0)
+#define SG4D_TRACE(cond, slot) do { } while (0)
 #endif
 
 template <int N, int PMODE, int EMODE, int PT>
@@ -270,6 +279,7 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    SG4D_TRACE_INIT();
     const int K = p.op.ncols;
     const int nkb = (K + kKB - 1) / kKB;
     const long long ntiles = (p.R + kTileM - 1) / kTileM;
@@ -364,7 +374,9 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                 load_idx(tile + 2LL * gridDim.x, ib);
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int stage = (int)(it % kStages);
+                    SG4D_TRACE(tid == 0 && it < 400, it * 5);
                     mbar_wait_warp<40>(lane, bar_empty + 8 * stage, ((it / kStages) & 1u) ^ 1u);
+                    SG4D_TRACE(tid == 0 && it < 400, it * 5 + 1);
                     uint8_t *st = smem + stage * SM::kStageBytes;
                     weights_tma(stage, kb);
                     const int col = kb * kKB + 4 * c;
@@ -381,9 +393,12 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                         v.z = ok ? fmaxf(v.z, 0.f) : 0.f, v.w = ok ? fmaxf(v.w, 0.f) : 0.f;
                         put(st, r, v);
                     }
+                    SG4D_TRACE(tid == 0 && it < 400, it * 5 + 2);
                     tc::fence_proxy_async_smem();
                     __syncwarp();
+                    SG4D_TRACE(tid == 0 && it < 400, it * 5 + 3);
                     if (lane == 0) tc::mbar_arrive(bar_full + 8 * stage);
+                    SG4D_TRACE(tid == 0 && it < 400, it * 5 + 4);
                 }
 #pragma unroll
                 for (int i = 0; i < kProdRows; ++i)
@@ -438,7 +453,9 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                     const long long tile = tile_t;
                     const int kb = kb_t;
                     const int stage = (int)(it % kStages);
+                    SG4D_TRACE(tid == 0 && it < 400, it * 5);
                     mbar_wait_warp<40>(lane, bar_empty + 8 * stage, ((it / kStages) & 1u) ^ 1u);
+                    SG4D_TRACE(tid == 0 && it < 400, it * 5 + 1);
                     uint8_t *st = smem + stage * SM::kStageBytes;
                     weights_tma(stage, kb);
                     const int col = kb * kKB + 4 * c;
@@ -447,9 +464,12 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                         const int r = r0 + (PT / 8) * i;
                         put(st, r, op_apply<(PMODE == 5 ? 0 : PMODE)>(p.op, buf[j][i], tile * kTileM + r, p.R, col, s_s, s_t, s_p));
                     }
+                    SG4D_TRACE(tid == 0 && it < 400, it * 5 + 2);
                     tc::fence_proxy_async_smem();   // my smem writes -> visible to the tensor core (async proxy)
                     __syncwarp();
+                    SG4D_TRACE(tid == 0 && it < 400, it * 5 + 3);
                     if (lane == 0) tc::mbar_arrive(bar_full + 8 * stage);
+                    SG4D_TRACE(tid == 0 && it < 400, it * 5 + 4);
                     issue(buf[j]);   // refill this ring slot
                     if (++kb_t == nkb) kb_t = 0, tile_t += gridDim.x;
                     ++it;
@@ -464,12 +484,16 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
         long long ti = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
             const int acc = (int)(ti & 1);
+            SG4D_TRACE(lane == 0 && ti < 256, 4096 + (int)ti * 2);
             mbar_wait_warp<32>(lane, bar_tempty + 8 * acc, (uint32_t)(((ti >> 1) & 1) ^ 1));
+            SG4D_TRACE(lane == 0 && ti < 256, 4096 + (int)ti * 2 + 1);
             tc::tc_fence_after_sync();
             const uint32_t d_tmem = tmem + (uint32_t)(acc * N);
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int stage = (int)(it % kStages);
+                SG4D_TRACE(lane == 0 && it < 400, 2048 + it * 3);
                 mbar_wait_warp<40>(lane, bar_full + 8 * stage, (uint32_t)((it / kStages) & 1));
+                SG4D_TRACE(lane == 0 && it < 400, 2048 + it * 3 + 1);
                 tc::tc_fence_after_sync();
                 if (lane == 0) {
                     const uint32_t a_hi = smem_base + stage * SM::kStageBytes, a_lo = a_hi + SM::kABytes;
@@ -485,6 +509,7 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                     tc::umma_commit(bar_empty + 8 * stage);                      // smem stage free when these finish
                     if (kb == nkb - 1) tc::umma_commit(bar_tfull + 8 * acc);     // accumulator ready
                 }
+                SG4D_TRACE(lane == 0 && it < 400, 2048 + it * 3 + 2);
                 __syncwarp();
             }
         }
@@ -528,7 +553,9 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                 const long long rown = row + (long long)gridDim.x * kTileM;
                 ixn = rown < p.R ? __ldg(p.op.g.idx + rown) : 0;
             }
+            SG4D_TRACE(e == 0 && ti < 256, 5120 + (int)ti * 5);
             mbar_wait_warp<128>(lane, bar_tfull + 8 * acc, (uint32_t)((ti >> 1) & 1));
+            SG4D_TRACE(e == 0 && ti < 256, 5120 + (int)ti * 5 + 1);
             tc::tc_fence_after_sync();
             // two 32-column chunks per wait: the second tcgen05.ld overlaps the first one's latency
             if constexpr (EMODE == 3) {
@@ -571,6 +598,7 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 
+            SG4D_TRACE(e == 0 && ti < 256, 5120 + (int)ti * 5 + 2);
             const long long row0 = tile * kTileM;
             const int nvalid = SG4D_DBG(p.dbg_no_epi) ? 0 : (int)min((long long)kTileM, p.R - row0);
             constexpr int kVecPerRow = N / 4;
@@ -638,6 +666,7 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                     *reinterpret_cast<float4 *>(p.Y + (row0 + r) * p.ldy + p.ycol0 + cc) = v;
                 }
             }
+            SG4D_TRACE(e == 0 && ti < 256, 5120 + (int)ti * 5 + 3);
             if (EMODE == 0) {   // per-channel statistics (+ group max/min) by the column owners
                 const int smask = p.S > 0 ? p.S - 1 : 0;
                 float s = 0.f, sq = 0.f;
@@ -702,6 +731,7 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                 }
                 dacc[0] += (double)s, dacc[1] += (double)sq;
             }
+            SG4D_TRACE(e == 0 && ti < 256, 5120 + (int)ti * 5 + 4);
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // Cs is reused by the next tile
         }
         if constexpr (EMODE == 3) {
@@ -1952,3 +1982,9 @@ extern "C" int sg4d_dense_pool_bwd_dw(long long rows, int m, int n, int group, c
     dense_wgrad_reduce_kernel<<<(m * n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(grid, m, n, 128, nnb, partial, dw, n);
     return SG4D_LAUNCH_CHECK();
 }
+
+#ifdef SG4D_DEBUG
+extern "C" int sg4d_debug_set_trace(unsigned long long *buf) {
+    return status_of(cudaMemcpyToSymbol(sg4d::g_trace, &buf, sizeof(buf)));
+}
+#endif
