@@ -63,13 +63,16 @@ SIGNATURES = {
     "sg4d_dense_bwd_dx": [_i64, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _i, _p, _p],
     "sg4d_dense_bwd_dw": [_i64, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p],
     "sg4d_dense_pool_bwd_dw": [_i64, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "sg4d_frontend_objects": [_i, _i, _i, _p, _p, _f, _p, _p, _p, _p, _p],
+    "sg4d_frontend_edges": [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "sg4d_frontend_sample": [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "sg4d_inner_bwd_dw_grouped": [_i64] + [_i] * 7 + [_p] * 4 + [_i] + [_p] * 7 + [_i, _p],
 }
 OTHER_SYMBOLS = ["sg4d_abi_version", "sg4d_error_string", "sg4d_check_device", "sg4d_mlp_grid",
                  "sg4d_weight_image_floats", "sg4d_wgrad_partial_floats", "sg4d_mlp_partial_doubles", "sg4d_pool_bwd_prologue_parts", "sg4d_spatial_index_bytes",
                  "sg4d_spatial_index_supported", "sg4d_sa_moments_parts", "sg4d_sa1_s1part_doubles",
                  "sg4d_dense_weight_floats", "sg4d_dense_partial_doubles", "sg4d_colsum_part_doubles",
-                 "sg4d_dense_wgrad_partial_floats"]
+                 "sg4d_dense_wgrad_partial_floats", "sg4d_frontend_workspace_bytes"]
 
 _lib = None
 
@@ -102,6 +105,7 @@ def load():
         lib.sg4d_dense_partial_doubles.argtypes, lib.sg4d_dense_partial_doubles.restype = [_i64, _i], _i64
         lib.sg4d_colsum_part_doubles.argtypes, lib.sg4d_colsum_part_doubles.restype = [_i64, _i], _i64
         lib.sg4d_dense_wgrad_partial_floats.argtypes, lib.sg4d_dense_wgrad_partial_floats.restype = [_i64, _i, _i], _i64
+        lib.sg4d_frontend_workspace_bytes.argtypes, lib.sg4d_frontend_workspace_bytes.restype = [_i, _i, _i], _i64
         if lib.sg4d_abi_version() != 1:
             raise RuntimeError("libsg4d.so ABI version mismatch; rebuild it")
         _lib = lib

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 SO = os.path.join(HERE, "libsg4d.so")
-SOURCES = ["fps.cu", "ball_query.cu", "group.cu", "gnn.cu", "mlp.cu", "spatial.cu", "interpolate.cu"]
+SOURCES = ["fps.cu", "ball_query.cu", "group.cu", "gnn.cu", "mlp.cu", "spatial.cu", "interpolate.cu", "frontend.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

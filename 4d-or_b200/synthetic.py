@@ -117,3 +117,26 @@ def to_device(batch, device, non_blocking=False):
                 v = v.to(device, non_blocking=non_blocking)
         out[k] = v
     return out
+
+
+def make_raw_scene(scene_id, n_obj=12, n_points=200000, background=0.3):
+    """A raw scene for the crop / sample front-end (sg4d.frontend): points (P, 6) = xyz in metres + rgb, and per-point object
+    masks (P,) int32 (0 = unlabelled, i + 1 = object i) -- the inputs of the reference's data_preparation
+    (SGH/dataset/data_preparation_utils.py:52-76).  Objects are Gaussian blobs in a 4 m room, point counts drawn unevenly."""
+    gen = torch.Generator().manual_seed(99000 + int(scene_id))
+    share = torch.rand(n_obj, generator=gen) + 0.2
+    n_bg = int(n_points * background)
+    counts = (share / share.sum() * (n_points - n_bg)).long()
+    counts[0] += n_points - n_bg - int(counts.sum())
+    pts, masks = [], []
+    for i in range(n_obj):
+        c = 0.5 + 3.0 * torch.rand(3, generator=gen)
+        s = 0.1 + 0.25 * torch.rand(3, generator=gen)
+        pts.append(c + s * torch.randn(int(counts[i]), 3, generator=gen))
+        masks.append(torch.full((int(counts[i]),), i + 1, dtype=torch.int32))
+    pts.append(4.0 * torch.rand(n_bg, 3, generator=gen))
+    masks.append(torch.zeros(n_bg, dtype=torch.int32))
+    xyz, m = torch.cat(pts), torch.cat(masks)
+    perm = torch.randperm(n_points, generator=gen)          # scanner order: objects are interleaved
+    points = torch.cat([xyz, torch.rand(n_points, 3, generator=gen)], dim=1)[perm].contiguous()
+    return points, m[perm].contiguous()

@@ -380,6 +380,30 @@ int sg4d_dense_pool_bwd_dw(long long rows, int m, int n, int group, const float 
                            const float *dsel, const uint8_t *garg, const float *y1, const float *s1, const float *t1,
                            float *partial, float *dw, sg4d_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Section 6 -- crop / sample front-end: one scene (points (P, stride) fp32 with xyz first, per-point
+ * object masks: 0 = none, i + 1 = object i) -> the per-object and per-edge clouds the encoders consume.  Replaces the numpy /
+ * open3d loop of SGH/dataset/data_preparation_utils.py:104-125 (objects), :178-218 (edges), :12-18 (zero_mean), :37-39 (the
+ * replace=True draw).  Draws are an input: index = candidates[min(floor(u * len), len - 1)], candidates in ascending point order.
+ * ---------------------------------------------------------------------------------------------- */
+long long sg4d_frontend_workspace_bytes(int P, int nobj, int E);
+/* obj_list (nobj, P) int32: members of every object in ascending point index; totals (nobj + 1): [0] unlabelled, [i + 1] members
+ * of object i; obj_box (nobj, 6): {min xyz - padding, max xyz + padding}.  nobj <= 31. */
+int sg4d_frontend_objects(int P, int stride, int nobj, const float *pts, const int32_t *masks, float padding, void *ws,
+                          int32_t *obj_list, int *totals, float *obj_box, sg4d_stream_t stream);
+/* edges (2, E) int64 (subject, object) object indices; edge_box (E, 6) = union of the two padded boxes; edge_list (E, P): points
+ * STRICTLY inside it, ascending; edge_totals (E, 2): [e][1] = their number. */
+int sg4d_frontend_edges(int P, int stride, int E, const float *pts, const int32_t *masks, const int64_t *edges,
+                        const float *obj_box, void *ws, int32_t *edge_list, int *edge_totals, float *edge_box,
+                        sg4d_stream_t stream);
+/* out (clouds, n, fout): drawn points [xyz | features | (edges only) 1 / 2 for points of the subject / object instance], xyz
+ * centred and scaled to the unit sphere; fout = stride (+ 1 with edges).  list / totals as written by the two calls above
+ * (edges == NULL: object clouds).  picked (clouds, n) original point indices (may be NULL); mean (clouds, 3); dist (clouds);
+ * scratch: clouds * (ceil(n / 256) * 24 + 4) bytes. */
+int sg4d_frontend_sample(int P, int stride, int clouds, int n, const float *pts, const int32_t *masks, const int32_t *list,
+                         const int *totals, const int64_t *edges, const float *u, float *out, int32_t *picked, float *mean,
+                         float *dist, void *scratch, sg4d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
