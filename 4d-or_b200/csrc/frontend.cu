@@ -125,82 +125,84 @@ __global__ void fe_union_kernel(int E, const int64_t *__restrict__ edges, const 
     }
 }
 
-// draw + gather: out[c][j] = [xyz, features (fin - 3)[, edge mask]] of point list[c][min(floor(u * len), len - 1)], and the
-// per-block partial sums of xyz for the centroid.  grid = (ceil(N / 256), clouds); part (clouds, gridDim.x, 3) fp64.
+// the draw: index of sample j of cloud c in the scene, or -1 for an empty candidate list
+__device__ __forceinline__ int fe_pick(const int32_t *__restrict__ list, int P, int len, const float *__restrict__ u, int c, int N, int j) {
+    if (len <= 0) return -1;
+    int k = (int)(u[(size_t)c * N + j] * (float)len);      // fp32 product, truncated: the restatement does the same
+    k = k < len - 1 ? k : len - 1;
+    return list[(size_t)c * P + k];
+}
+
+// Three passes over the DRAWS (the scene itself is a few MB and stays in L2; the 171 MB of crops are written exactly once):
+//   PASS 0  per-block fp64 partial sums of the drawn xyz                      -> centroid (fe_mean_kernel)
+//   PASS 1  per-cloud max squared norm of (xyz - centroid)                    -> unit-sphere scale
+//   PASS 2  write [ (xyz - centroid) / dist | features | edge mask ] and the picked indices
+// grid = (ceil(N / 256), clouds).
+template <int PASS>
 __global__ void __launch_bounds__(256)
-fe_gather_kernel(FeSrc s, const int32_t *__restrict__ list, const int *__restrict__ totals, int tot_stride, int tot_off,
-                 const float *__restrict__ u, int N, int fout, const int64_t *__restrict__ edges, int E,
-                 float *__restrict__ out, int32_t *__restrict__ picked, double *__restrict__ part) {
+fe_sample_kernel(FeSrc s, const int32_t *__restrict__ list, const int *__restrict__ totals, int tot_stride, const float *__restrict__ u,
+                 int N, int fout, const int64_t *__restrict__ edges, int E, const float *__restrict__ mean,
+                 unsigned *__restrict__ maxn2, double *__restrict__ part, float *__restrict__ out, int32_t *__restrict__ picked,
+                 float *__restrict__ dist) {
     const int c = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
-    const int len = totals[c * tot_stride + tot_off];
-    double sx = 0.0, sy = 0.0, sz = 0.0;
-    if (j < N) {
-        float *o = out + ((size_t)c * N + j) * fout;
-        int i = -1;
-        if (len > 0) {
-            int k = (int)(u[(size_t)c * N + j] * (float)len);      // fp32 product, truncated: the restatement does the same
-            k = k < len - 1 ? k : len - 1;
-            i = list[(size_t)c * s.P + k];
-            const float *p = s.pts + (size_t)i * s.stride;
-            for (int a = 0; a < s.stride; ++a) o[a] = p[a];
-            if (edges) {      // 4th feature: 1 = point of the subject instance, 2 = of the object instance (:188-190)
-                const int m = s.masks[i];
-                o[s.stride] = m == (int)edges[c] + 1 ? 1.f : (m == (int)edges[E + c] + 1 ? 2.f : 0.f);
-            }
-            sx = p[0], sy = p[1], sz = p[2];
-        } else {
-            for (int a = 0; a < fout; ++a) o[a] = 0.f;
+    const int len = totals[c * tot_stride + 1];
+    const int i = j < N ? fe_pick(list, s.P, len, u, c, N, j) : -1;
+    const float *p = s.pts + (size_t)(i < 0 ? 0 : i) * s.stride;
+    if (PASS == 0) {
+        double sx = i >= 0 ? (double)p[0] : 0.0, sy = i >= 0 ? (double)p[1] : 0.0, sz = i >= 0 ? (double)p[2] : 0.0;
+        __shared__ double sh[8][3];
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            sx += __shfl_xor_sync(0xffffffffu, sx, off), sy += __shfl_xor_sync(0xffffffffu, sy, off), sz += __shfl_xor_sync(0xffffffffu, sz, off);
         }
-        if (picked) picked[(size_t)c * N + j] = i;
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][0] = sx, sh[threadIdx.x >> 5][1] = sy, sh[threadIdx.x >> 5][2] = sz;
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += sh[w][threadIdx.x];
+            part[((size_t)c * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = t;
+        }
+        return;
     }
-    __shared__ double sh[8][3];
+    const float m0 = mean[c * 3], m1 = mean[c * 3 + 1], m2 = mean[c * 3 + 2];
+    const float x = i >= 0 ? p[0] - m0 : 0.f, y = i >= 0 ? p[1] - m1 : 0.f, z = i >= 0 ? p[2] - m2 : 0.f;   // point -= mean (:14)
+    if (PASS == 1) {
+        float n2 = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));    // pow(2).sum(1), left to right
 #pragma unroll
-    for (int off = 16; off; off >>= 1) {
-        sx += __shfl_xor_sync(0xffffffffu, sx, off), sy += __shfl_xor_sync(0xffffffffu, sy, off), sz += __shfl_xor_sync(0xffffffffu, sz, off);
+        for (int off = 16; off; off >>= 1) n2 = fmaxf(n2, __shfl_xor_sync(0xffffffffu, n2, off));
+        if ((threadIdx.x & 31) == 0) atomicMax(maxn2 + c, __float_as_uint(n2));   // non-negative floats order like their bits
+        return;
     }
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][0] = sx, sh[threadIdx.x >> 5][1] = sy, sh[threadIdx.x >> 5][2] = sz;
-    __syncthreads();
-    if (threadIdx.x < 3) {
-        double t = 0.0;
-        for (int w = 0; w < 8; ++w) t += sh[w][threadIdx.x];
-        part[((size_t)c * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = t;
-    }
-}
-
-// zero_mean (:12-18), pass 1: subtract the centroid (fp32 mean, as torch.mean returns it), per-cloud max squared norm
-__global__ void __launch_bounds__(256)
-fe_center_kernel(int N, int fout, int nparts, const double *__restrict__ part, float *__restrict__ out, float *__restrict__ mean,
-                 unsigned *__restrict__ maxn2) {
-    const int c = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
-    __shared__ float m[3];
-    if (threadIdx.x < 3) {
-        double t = 0.0;
-        for (int q = 0; q < nparts; ++q) t += part[((size_t)c * nparts + q) * 3 + threadIdx.x];
-        m[threadIdx.x] = (float)(t / (double)N);
-        if (blockIdx.x == 0) mean[c * 3 + threadIdx.x] = m[threadIdx.x];
-    }
-    __syncthreads();
-    float n2 = 0.f;
-    if (j < N) {
-        float *o = out + ((size_t)c * N + j) * fout;
-        const float x = o[0] - m[0], y = o[1] - m[1], z = o[2] - m[2];
-        o[0] = x, o[1] = y, o[2] = z;
-        n2 = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));    // pow(2).sum(1), left to right
-    }
-#pragma unroll
-    for (int off = 16; off; off >>= 1) n2 = fmaxf(n2, __shfl_xor_sync(0xffffffffu, n2, off));
-    if ((threadIdx.x & 31) == 0) atomicMax(maxn2 + c, __float_as_uint(n2));   // non-negative floats order like their bits
-}
-
-// pass 2: divide by the largest distance (sqrt of the max squared norm: sqrt is monotone, so max(sqrt) = sqrt(max))
-__global__ void __launch_bounds__(256)
-fe_scale_kernel(int N, int fout, const unsigned *__restrict__ maxn2, float *__restrict__ out, float *__restrict__ dist) {
-    const int c = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
+    // sqrt is monotone: max over rows of sqrt(n2) = sqrt(max n2) (:16)
     const float d = sqrtf(__uint_as_float(maxn2[c]));
     if (blockIdx.x == 0 && threadIdx.x == 0) dist[c] = d;
-    if (j < N) {
-        float *o = out + ((size_t)c * N + j) * fout;
-        o[0] = __fdiv_rn(o[0], d), o[1] = __fdiv_rn(o[1], d), o[2] = __fdiv_rn(o[2], d);
+    if (j >= N) return;
+    float *o = out + ((size_t)c * N + j) * fout;
+    if (i < 0) {
+        for (int a = 0; a < fout; ++a) o[a] = 0.f;
+    } else {
+        o[0] = __fdiv_rn(x, d), o[1] = __fdiv_rn(y, d), o[2] = __fdiv_rn(z, d);             // point /= furthest_distance (:17)
+        for (int a = 3; a < s.stride; ++a) o[a] = p[a];
+        if (edges) {      // 4th feature: 1 = point of the subject instance, 2 = of the object instance (:188-190)
+            const int m = s.masks[i];
+            o[s.stride] = m == (int)edges[c] + 1 ? 1.f : (m == (int)edges[E + c] + 1 ? 2.f : 0.f);
+        }
+    }
+    if (picked) picked[(size_t)c * N + j] = i;
+}
+
+// centroid of every cloud: fp64 sum of the per-block partials in a fixed order (one warp per cloud), rounded once to fp32
+__global__ void fe_mean_kernel(int N, int nparts, const double *__restrict__ part, float *__restrict__ mean) {
+    const int c = blockIdx.x, lane = threadIdx.x;
+    double t[3] = {0.0, 0.0, 0.0};
+    for (int q = lane; q < nparts; q += 32)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) t[a] += part[((size_t)c * nparts + q) * 3 + a];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int off = 16; off; off >>= 1) t[a] += __shfl_xor_sync(0xffffffffu, t[a], off);
+        if (lane == 0) mean[c * 3 + a] = (float)(t[a] / (double)N);
     }
 }
 
@@ -265,8 +267,11 @@ extern "C" int sg4d_frontend_sample(int P, int stride, int clouds, int n, const 
     cudaError_t e = cudaMemsetAsync(maxn2, 0, (size_t)clouds * 4, st);
     if (e != cudaSuccess) return status_of(e);
     FeSrc s{pts, masks, P, stride, nullptr};
-    fe_gather_kernel<<<dim3(nb, clouds), 256, 0, st>>>(s, list, totals, edges ? 2 : 1, 1, u, n, fout, edges, clouds, out, picked, part);
-    fe_center_kernel<<<dim3(nb, clouds), 256, 0, st>>>(n, fout, nb, part, out, mean, maxn2);
-    fe_scale_kernel<<<dim3(nb, clouds), 256, 0, st>>>(n, fout, maxn2, out, dist);
+    const int ts = edges ? 2 : 1;
+    const int *tot = edges ? totals : totals;      // objects: entry c + 1 = totals[c * 1 + 1]; edges: totals[c * 2 + 1]
+    fe_sample_kernel<0><<<dim3(nb, clouds), 256, 0, st>>>(s, list, tot, ts, u, n, fout, edges, clouds, mean, maxn2, part, out, picked, dist);
+    fe_mean_kernel<<<clouds, 32, 0, st>>>(n, nb, part, mean);
+    fe_sample_kernel<1><<<dim3(nb, clouds), 256, 0, st>>>(s, list, tot, ts, u, n, fout, edges, clouds, mean, maxn2, part, out, picked, dist);
+    fe_sample_kernel<2><<<dim3(nb, clouds), 256, 0, st>>>(s, list, tot, ts, u, n, fout, edges, clouds, mean, maxn2, part, out, picked, dist);
     return SG4D_LAUNCH_CHECK();
 }

@@ -59,6 +59,9 @@ def parse():
                          "fwd+bwd; 3 = 8 scenes, full pipeline (default, the headline); 4 = 32 scenes + image branch; "
                          "5 = 32 scenes per GPU (256 at 8 GPUs)")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's own code on the GPU")
+    ap.add_argument("--e2e-input", default="scene", choices=["scene", "crops", "both"],
+                    help="what the end-to-end leg uploads every step: raw scenes (GPU front-end builds the crops) or the crops")
+    ap.add_argument("--scene-points", type=int, default=200000, help="points per raw scene of the end-to-end leg")
     a = ap.parse_args()
     a.forward_only, a.encoders_only, a.image = False, False, False
     if a.config == 1:
@@ -343,32 +346,91 @@ def main_sg4d(args):
     ms_per_step = total_ms / args.steps
     value = world * S / (ms_per_step / 1e3)
 
-    # ---- timed region 2: end to end through the public API, host (pinned) buffers in, loss out
-    e2e = None
-    if not args.no_e2e:
-        losses = []
-        pf = parallel.DevicePrefetcher(dev)
-        for _ in range(2):                      # untimed: allocates the two device staging buffers
-            pf.submit(pinned)
-            step(pf.next())
+    # ---- timed region 2: end to end through the public API, host (pinned) buffers in, loss out.
+    #      Default input = RAW SCENES (points + per-point object masks, --scene-points each): every step uploads its S scenes
+    #      (a few MB each) from pinned host memory and the GPU front-end (sg4d.frontend: crops, union boxes, sampling, zero_mean)
+    #      builds the 12 + 66 clouds of --points points per scene on the device -- the step immediately before the hot path
+    #      in the reference (SGH/dataset/data_preparation_utils.py), there on the CPU.  --e2e-input crops uploads the
+    #      pre-cropped clouds instead (171 MB per scene; round 1's path).
+    def timed_e2e(make_batch, h2d):
+        for _ in range(2):                      # untimed: allocations
+            step(make_batch(0))
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        pf.submit(pinned)                       # every step's upload happens inside the timed region ...
         for i in range(args.steps):
-            batch = pf.next()
-            if i + 1 < args.steps:
-                pf.submit(pinned)               # ... the next one overlapping this step's kernels (side stream)
-            losses.append(step(batch).detach().to("cpu", non_blocking=False))
-            if os.environ.get("SG4D_BENCH_DEBUG"):
-                print(f"e2e step {i}: t={time.perf_counter():.4f}", file=sys.stderr)
+            step(make_batch(i)).detach().to("cpu", non_blocking=False)       # loss read back every step
         e1.record()
         barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * S / (float(t.item()) / args.steps / 1e3), "unit": "scenes/s",
-               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4}
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return {"value": world * S / (float(tt.item()) / args.steps / 1e3), "unit": "scenes/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+
+    e2e = e2e_crops = None
+    if not args.no_e2e:
+        if args.e2e_input in ("scene", "both"):
+            from sg4d import frontend
+            raw = [synthetic.make_raw_scene(rank * S + i, n_obj=args.n_obj, n_points=args.scene_points) for i in range(S)]
+            raw_pts = torch.stack([r[0] for r in raw]).pin_memory()           # (S, P, 6)
+            raw_msk = torch.stack([r[1] for r in raw]).pin_memory()           # (S, P)
+            small = {k: pinned[k] for k in ("relation_objects_one_hot", "gt_class", "gt_rels") + (("full_image_features",) if args.image else ())}
+            side = torch.cuda.Stream(device=dev)
+            bufs = [None, None]
+
+            def stage(slot):
+                """step i + 1's scenes: upload AND crop on the side stream while step i computes on the main stream (the
+                front-end's kernels are small latency-bound grids without shared memory: they co-reside with the MLP kernels)"""
+                with torch.cuda.stream(side):
+                    pts_d, msk_d = raw_pts.to(dev, non_blocking=True), raw_msk.to(dev, non_blocking=True)
+                    sm = {k: v.to(dev, non_blocking=True) for k, v in small.items()}
+                    scenes = [frontend.prepare_scene(pts_d[k], msk_d[k], args.n_obj, args.points, pr, pairs=args.pairs) for k in range(S)]
+                    b = {"obj_points": torch.cat([sc["obj_points"].permute(0, 2, 1) for sc in scenes]).permute(0, 2, 1),
+                         "rel_points": torch.cat([sc["rel_points"].permute(0, 2, 1) for sc in scenes]).permute(0, 2, 1),
+                         "edge_indices": resident["edge_indices"]}
+                    b.update(sm)
+                    if "edge_scene" in resident:
+                        b["edge_scene"] = resident["edge_scene"]
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                bufs[slot] = (b, ev)
+
+            def scene_batch(i):
+                if bufs[i & 1] is None:
+                    stage(i & 1)
+                b, ev = bufs[i & 1]
+                main = torch.cuda.current_stream(dev)
+                main.wait_event(ev)
+                for v in b.values():
+                    if torch.is_tensor(v):
+                        v.record_stream(main)
+                side.wait_stream(main)              # the slot being refilled was last read by the previous step
+                stage((i + 1) & 1)
+                return b
+
+            h2d_scene = raw_pts.numel() * 4 + raw_msk.numel() * 4 + sum(v.numel() * v.element_size() for v in small.values())
+            e2e = timed_e2e(scene_batch, h2d_scene)
+            e2e["input"] = f"{S} raw scenes of {args.scene_points} points + object masks per step; crops built by the GPU front-end"
+            bufs = [None, None]
+        if args.e2e_input in ("crops", "both"):
+            pf = parallel.DevicePrefetcher(dev)
+            state = {"primed": False}
+
+            def crops_batch(i):
+                if not state["primed"]:
+                    pf.submit(pinned)
+                    state["primed"] = True
+                b = pf.next()
+                pf.submit(pinned)
+                return b
+
+            r = timed_e2e(crops_batch, h2d_bytes)
+            r["input"] = "pre-cropped clouds uploaded every step"
+            if e2e is None:
+                e2e = r
+            else:
+                e2e_crops = r
 
     if rank != 0:
         if world > 1:
@@ -573,7 +635,7 @@ def main_sg4d(args):
                        "l2": f"inputs are {h2d_bytes / 1e6:.0f} MB per step per GPU (> 126 MB L2), no flush needed",
                        "peak_memory_gb": round(peak_mem_gb, 2),
                        "cpu_sample": cpu["sample"] if cpu else None},
-            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
+            "clocks": clk.summary(), "e2e": e2e, "e2e_crops": e2e_crops, "gpu_launches": launches,
             "roofline": roof, "cpu_baseline": cpu, "gpu_reference": gpu_ref,
             "kernel_table": {"ms_per_step": table_ms_per_step, "own_kernel_ms_per_step": own_ms,
                              "note": "second pass of the same steps, one stream, CUDA events around every C-ABI call"},
