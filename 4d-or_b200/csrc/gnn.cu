@@ -34,22 +34,41 @@ triplet_gather_kernel(long long total4, int d4, int de4, const float4 *__restric
 
 // out[v, col] = sum_{p in [seg_ptr[v], seg_ptr[v+1])} ( src[order[p]*stride + col0 + col]
 //                                                     (+ src[order[p]*stride + col1 + col]) )
+// Warp-segmented: one warp per (node, 128-column chunk); the lanes own one float4 column group each, so every edge row is
+// one coalesced 512-byte read, and the node's (destination-sorted) edge segment is walked in its fixed order -- the sum is
+// deterministic, unlike torch_scatter's atomics (network_TripletGCN.py:57).  Two edges are in flight per step.
 __global__ void __launch_bounds__(256)
-segment_sum_kernel(long long total, int d, long long stride, int col0, int col1, int has_second,
+segment_sum_kernel(int n_nodes, int d, long long stride, int col0, int col1, int has_second,
                    const float *__restrict__ src, const int32_t *__restrict__ order,
                    const int32_t *__restrict__ seg_ptr, float *__restrict__ out) {
-    for (long long t = blockIdx.x * 256LL + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
-        const long long v = t / d;
-        const int col = (int)(t - v * d);
+    const int lane = threadIdx.x & 31;
+    const int chunks = (d + 127) / 128;
+    const long long nwarp = ((long long)gridDim.x * 256) >> 5;
+    for (long long w = (blockIdx.x * 256LL + threadIdx.x) >> 5; w < (long long)n_nodes * chunks; w += nwarp) {
+        const int v = (int)(w / chunks), col = (int)(w % chunks) * 128 + lane * 4;
+        if (col >= d) continue;
         const int p0 = __ldg(seg_ptr + v), p1 = __ldg(seg_ptr + v + 1);
-        float acc = 0.f;
-        for (int p = p0; p < p1; ++p) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto row_val = [&](int p) {
             const float *row = src + (long long)__ldg(order + p) * stride;
-            float a = __ldg(row + col0 + col);
-            if (has_second) a += __ldg(row + col1 + col);  // new_x_i + new_x_j (:48-51)
-            acc += a;
+            float4 a = __ldg(reinterpret_cast<const float4 *>(row + col0 + col));
+            if (has_second) {   // new_x_i + new_x_j (:48-51)
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(row + col1 + col));
+                a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+            }
+            return a;
+        };
+        int p = p0;
+        for (; p + 1 < p1; p += 2) {
+            const float4 a = row_val(p), b = row_val(p + 1);     // both loads issued before either is consumed
+            acc.x += a.x, acc.y += a.y, acc.z += a.z, acc.w += a.w;
+            acc.x += b.x, acc.y += b.y, acc.z += b.z, acc.w += b.w;
         }
-        out[t] = acc;
+        if (p < p1) {
+            const float4 a = row_val(p);
+            acc.x += a.x, acc.y += a.y, acc.z += a.z, acc.w += a.w;
+        }
+        *reinterpret_cast<float4 *>(out + (long long)v * d + col) = acc;
     }
 }
 
@@ -81,12 +100,13 @@ extern "C" int sg4d_triplet_gather(int64_t n_edges, int d, int de, const float *
 extern "C" int sg4d_segment_sum(int n_nodes, int d, int64_t src_stride, int col0, int col1, const float *src,
                                 int has_second, const int32_t *order, const int32_t *seg_ptr, float *out,
                                 sg4d_stream_t stream) {
-    if (n_nodes < 0 || d <= 0 || src_stride < d || col0 < 0 || col1 < 0 || !src || !order || !seg_ptr || !out)
+    if (n_nodes < 0 || d <= 0 || (d & 3) || src_stride < d || (src_stride & 3) || col0 < 0 || col1 < 0 || (col0 & 3) || (col1 & 3) ||
+        !src || !order || !seg_ptr || !out || (reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
         return SG4D_EINVAL;
     if (n_nodes == 0) return SG4D_OK;
-    const long long total = (long long)n_nodes * d;
-    segment_sum_kernel<<<flat_grid(total), 256, 0, (cudaStream_t)stream>>>(total, d, src_stride, col0, col1,
-                                                                          has_second, src, order, seg_ptr, out);
+    const long long warps = (long long)n_nodes * ((d + 127) / 128);
+    segment_sum_kernel<<<flat_grid(warps * 32), 256, 0, (cudaStream_t)stream>>>(n_nodes, d, src_stride, col0, col1,
+                                                                               has_second, src, order, seg_ptr, out);
     return SG4D_LAUNCH_CHECK();
 }
 

@@ -111,12 +111,25 @@ class SGPNModelWrapper(nn.Module):
         loss_rel = F.nll_loss(rel_pred, batch['gt_rels'], weight=self.weights_rel.to(rel_pred.device))
         return self.mconfig['lambda_o'] * loss_obj + loss_rel
 
+    # per-take relation predictions for the epoch metrics (reference :113-132); set by the trainer (sg4d.metrics.RelationMetrics)
+    metrics = None
+
+    def update_metrics(self, batch, rel_pred, split='train'):
+        if self.metrics is not None:
+            self.metrics.update(batch, rel_pred, split)
+
+    def reset_metrics(self, split=None):
+        if self.metrics is not None:
+            self.metrics.reset(split)
+
     def training_step(self, batch, batch_idx=0):
         obj_pred, rel_pred = self(batch)
+        self.update_metrics(batch, rel_pred, 'train')
         return self.loss(obj_pred, rel_pred, batch)
 
     def validation_step(self, batch, batch_idx=0):
         obj_pred, rel_pred = self(batch)
+        self.update_metrics(batch, rel_pred, 'val')
         return self.loss(obj_pred, rel_pred, batch)
 
     def predict_step(self, batch, batch_idx=0, dataloader_idx=0):

@@ -8,14 +8,61 @@
   ``optimizer_states`` -- a reference checkpoint's ``state_dict`` loads into the sg4d model and vice versa,
 * resume from the newest ``epoch=<N>.ckpt`` (``find_checkpoint_path``).
 
-Multi-GPU: pass a ``parallel.GradBucket``; the gradients are all-reduced (mean) once per step.  The reference's
-``precision=16`` autocast / GradScaler is not reproduced: sg4d computes in fp32 (3xTF32 on the tensor cores).
+* per-epoch relation metrics with the reference's per-take bookkeeping (``metrics.RelationMetrics``: precision / recall / F1
+  per relation and take, macro and weighted averages; scene_graph_prediction_model.py:113-132,195-238),
+* ``precision=16``: dynamic loss scaling with ``torch.cuda.amp.GradScaler``'s semantics (``LossScaler``: what Lightning's
+  ``precision=16`` wraps around the optimizer step, SGP/main.py:64) for reduced-precision compute paths.
+
+Multi-GPU: pass a ``parallel.GradBucket``; the gradients are all-reduced (mean) once per step.
 """
 import glob
 import os
 import re
 
 import torch
+
+
+class LossScaler:
+    """Dynamic loss scaling with the defaults and update rule of ``torch.cuda.amp.GradScaler`` (init_scale 2**16, growth 2x
+    after 2000 consecutive finite steps, back-off 0.5 and a SKIPPED optimizer step when a gradient is inf / nan)."""
+
+    def __init__(self, init_scale=2.0 ** 16, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000, enabled=True):
+        self.scale_value, self.growth_factor, self.backoff_factor = float(init_scale), growth_factor, backoff_factor
+        self.growth_interval, self.enabled, self._good_steps = growth_interval, enabled, 0
+
+    def scale(self, loss):
+        return loss * self.scale_value if self.enabled else loss
+
+    def step(self, optimizer, params=None):
+        """Unscale the gradients in place, skip the step if any is non-finite, update the scale.  Returns True if stepped."""
+        if not self.enabled:
+            optimizer.step()
+            return True
+        params = [p for g in optimizer.param_groups for p in g["params"]] if params is None else list(params)
+        grads = [p.grad for p in params if p.grad is not None]
+        inv = 1.0 / self.scale_value
+        finite = torch.ones((), dtype=torch.bool, device=grads[0].device) if grads else None
+        for g in grads:
+            g.mul_(inv)
+            finite = finite & torch.isfinite(g).all()
+        ok = bool(finite) if grads else True          # one host read per step, like GradScaler's found_inf
+        if ok:
+            optimizer.step()
+            self._good_steps += 1
+            if self._good_steps == self.growth_interval:
+                self.scale_value *= self.growth_factor
+                self._good_steps = 0
+        else:
+            self.scale_value *= self.backoff_factor
+            self._good_steps = 0
+        return ok
+
+    def state_dict(self):
+        return {"scale": self.scale_value, "growth_factor": self.growth_factor, "backoff_factor": self.backoff_factor,
+                "growth_interval": self.growth_interval, "_growth_tracker": self._good_steps}
+
+    def load_state_dict(self, sd):
+        self.scale_value, self._good_steps = float(sd["scale"]), int(sd.get("_growth_tracker", 0))
 
 
 def find_checkpoint_path(log_dir):
@@ -63,13 +110,19 @@ def load_checkpoint(path, model, optimizer=None, map_location=None):
     return int(ckpt.get("epoch", -1)), int(ckpt.get("global_step", 0))
 
 
-def fit(model, train_batches, val_batches=None, max_epochs=1, log_dir=None, bucket=None, on_epoch_end=None):
+def fit(model, train_batches, val_batches=None, max_epochs=1, log_dir=None, bucket=None, on_epoch_end=None, precision=32,
+        metrics=None):
     """Trains ``model`` (anything with ``training_step`` / ``validation_step`` / ``configure_optimizers``).
 
     ``train_batches`` / ``val_batches``: callables returning an iterable of batch dicts for one epoch (device
-    tensors), or plain iterables.  Returns a list of per-epoch dicts (mean train / val loss).
+    tensors), or plain iterables.  ``precision=16``: dynamic loss scaling (``LossScaler``).  ``metrics``: a
+    ``metrics.RelationMetrics``; the model's steps then record their relation predictions per take and every epoch record
+    gets ``train_macro_f1`` / ``val_macro_f1`` (the reference's Epoch_Macro/*_F1).  Returns a list of per-epoch dicts.
     """
     optimizer = model.configure_optimizers()
+    scaler = LossScaler(enabled=(precision == 16))
+    if metrics is not None:
+        model.metrics = metrics
     start_epoch, global_step = 0, 0
     if log_dir is not None:
         ckpt = find_checkpoint_path(log_dir)
@@ -92,12 +145,12 @@ def fit(model, train_batches, val_batches=None, max_epochs=1, log_dir=None, buck
             else:
                 optimizer.zero_grad(set_to_none=True)
             loss = model.training_step(batch, i)
-            loss.backward()
+            scaler.scale(loss).backward()
             if bucket is not None:
                 if bucket._hooks:
                     bucket.drop_unused()
                 bucket.all_reduce_mean()
-            optimizer.step()
+            scaler.step(optimizer)
             global_step += 1
             tot, cnt = loss.detach() if tot is None else tot + loss.detach(), cnt + 1
         rec = {"epoch": epoch, "train_loss": (float(tot) if tot is not None else 0.0) / max(cnt, 1), "global_step": global_step}
@@ -108,6 +161,12 @@ def fit(model, train_batches, val_batches=None, max_epochs=1, log_dir=None, buck
                 for i, batch in enumerate(batches_of(val_batches)):
                     vt, vc = vt + float(model.validation_step(batch, i)), vc + 1
             rec["val_loss"] = vt / max(vc, 1)
+        if metrics is not None:
+            rec["train_macro_f1"] = metrics.evaluate("train")["macro_f1"]
+            metrics.reset("train")
+            if val_batches is not None:
+                rec["val_macro_f1"] = metrics.evaluate("val")["macro_f1"]
+                metrics.reset("val")
         if log_dir is not None:
             save_checkpoint(os.path.join(log_dir, "checkpoints", f"epoch={epoch}.ckpt"), model, optimizer, epoch, global_step)
         if on_epoch_end is not None:

@@ -248,3 +248,53 @@ def test_trainer_fit_checkpoint_roundtrip(cuda, tmp_path):
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     hist2 = trainer.fit(m2, scenes, None, max_epochs=3, log_dir=str(tmp_path))
     assert [h["epoch"] for h in hist2] == [2]
+
+
+def test_three_adamw_steps_match_oracle(cuda):
+    """Trainer parity: three AdamW steps (lr = LR, weight_decay = W_DECAY, scene_graph_prediction_model.py:
+    240-242) on three scenes with sg4d and with the CPU oracle + torch.optim.AdamW from the same weights.  Adam normalises
+    every gradient entry to a step of ~lr, so an entry whose gradient is rounding noise (e.g. a Linear bias in front of a
+    BatchNorm: exactly 0 in sg4d, +-1e-9 in autograd) may move by lr per step in either direction: the bound is 2 * 3 * lr on
+    every entry, and the bulk of every large weight matrix must agree to 1e-6."""
+    from sg4d import synthetic
+    sd = weights.synth_state_dict(seed=6)
+    m = _model(cuda, sd, 0.1)
+    opt = m.configure_optimizers()
+    s = model_ref.clone_state(sd)
+    oparams = [v for v in s.values() if v.requires_grad]
+    oopt = torch.optim.AdamW(oparams, lr=m.lr, weight_decay=float(m.config["W_DECAY"]))
+    for i in range(3):
+        sc = synthetic.make_scene(50 + i, n_obj=4, n_points_obj=600, n_points_rel=700)
+        opt.zero_grad(set_to_none=True)
+        m.training_step(synthetic.to_device(sc, cuda)).backward()
+        opt.step()
+        oopt.zero_grad(set_to_none=True)
+        outs = model_ref.forward(s, sc, training=True, dropout=False)
+        model_ref.loss_fn(outs[0], outs[1], sc, torch.ones(12), torch.ones(15), 0.1).backward()
+        oopt.step()
+    lr = m.lr
+    moved = 0
+    for k, p_ in m.named_parameters():
+        if "fc_layer" in k:
+            continue
+        d = (p_.detach().cpu() - s[k].detach()).abs()
+        assert float(d.max()) <= 6 * lr + 1e-6, (k, float(d.max()))
+        if p_.numel() >= 4096:
+            assert float(d.median()) <= 1e-6, (k, float(d.median()))
+        moved += int(((p_.detach().cpu() - sd[k]).abs() > 0).sum())
+    assert moved > 1000000                                      # the weights did train
+
+
+def test_fit_records_macro_f1_and_loss_scaling(cuda, tmp_path):
+    """trainer.fit with the per-take relation metrics (reference :195-238) and precision=16 loss scaling (GradScaler rule)"""
+    from sg4d import metrics, synthetic, trainer
+    sd = weights.synth_state_dict(seed=4)
+    scenes = []
+    for i in range(3):
+        sc = synthetic.to_device(synthetic.make_scene(60 + i, n_obj=4, n_points_obj=600, n_points_rel=700), cuda)
+        sc["take_idx"] = i % 2
+        scenes.append(sc)
+    m = _model(cuda, sd, 0.1)
+    hist = trainer.fit(m, scenes, scenes[:1], max_epochs=1, precision=16, metrics=metrics.RelationMetrics(m.relationNames))
+    assert 0.0 <= hist[0]["train_macro_f1"] <= 1.0 and 0.0 <= hist[0]["val_macro_f1"] <= 1.0
+    assert torch.isfinite(torch.tensor(hist[0]["train_loss"]))

@@ -142,3 +142,44 @@ def test_spatial_index_workspace_contract():
     per_cloud = two - one                       # one more cloud: its index + its todo list
     assert per_cloud % 128 == 0 or (per_cloud - 4 * 1025) % 128 == 0
     assert lib.sg4d_spatial_index_bytes(0, 80000) in (0, 128) and lib.sg4d_spatial_index_bytes(3, 0) == 0
+
+
+def test_classification_report_matches_sklearn():
+    """sg4d.metrics.classification_report == sklearn's (what scene_graph_prediction_model.py:213-229 logs), incl. empty classes"""
+    import numpy as np
+    import torch
+    from sg4d import metrics
+    sk = __import__("pytest").importorskip("sklearn.metrics")
+    rng = np.random.RandomState(0)
+    gts, preds = rng.randint(0, 12, 500), rng.randint(0, 15, 500)       # labels 12..14 never occur as ground truth
+    names = [f"r{i}" for i in range(15)]
+    want = sk.classification_report(gts, preds, labels=list(range(15)), target_names=names, output_dict=True, zero_division=0)
+    got = metrics.classification_report(torch.from_numpy(gts), torch.from_numpy(preds), 15, names)
+    for key in names + ["macro avg", "weighted avg"]:
+        for f in ("precision", "recall", "f1-score"):
+            assert abs(got[key][f] - want[key][f]) < 1e-12, (key, f)
+    m = metrics.RelationMetrics(names)
+    for take in (3, 1):
+        m.update({"gt_rels": torch.from_numpy(gts[:100]), "take_idx": take}, torch.nn.functional.one_hot(torch.from_numpy(preds[:100]), 15).float())
+    ev = m.evaluate("train")
+    assert sorted(ev["takes"]) == [1, 3] and abs(ev["macro_f1"] - ev["takes"][1]["macro avg"]["f1-score"]) < 1e-12
+
+
+def test_loss_scaler_follows_grad_scaler_rule():
+    """LossScaler: unscaled gradients reach the optimizer, a non-finite gradient skips the step and halves the scale, the scale
+    doubles after `growth_interval` finite steps (torch.cuda.amp.GradScaler semantics, what Lightning's precision=16 applies)"""
+    import torch
+    from sg4d.trainer import LossScaler
+    w = torch.nn.Parameter(torch.tensor([1.0, -2.0]))
+    opt = torch.optim.SGD([w], lr=0.5)
+    sc = LossScaler(init_scale=8.0, growth_interval=2)
+    sc.scale((w * torch.tensor([3.0, 4.0])).sum()).backward()
+    assert torch.equal(w.grad, torch.tensor([24.0, 32.0]))
+    assert sc.step(opt) and torch.allclose(w.detach(), torch.tensor([1.0 - 1.5, -2.0 - 2.0])) and sc.scale_value == 8.0
+    w.grad = torch.tensor([float("inf"), 1.0])
+    before = w.detach().clone()
+    assert not sc.step(opt) and torch.equal(w.detach(), before) and sc.scale_value == 4.0
+    for _ in range(2):
+        w.grad = torch.ones(2)
+        sc.step(opt)
+    assert sc.scale_value == 8.0
