@@ -72,7 +72,8 @@ OTHER_SYMBOLS = ["sg4d_abi_version", "sg4d_error_string", "sg4d_check_device", "
                  "sg4d_weight_image_floats", "sg4d_wgrad_partial_floats", "sg4d_mlp_partial_doubles", "sg4d_pool_bwd_prologue_parts", "sg4d_spatial_index_bytes",
                  "sg4d_spatial_index_supported", "sg4d_sa_moments_parts", "sg4d_sa1_s1part_doubles",
                  "sg4d_dense_weight_floats", "sg4d_dense_partial_doubles", "sg4d_colsum_part_doubles",
-                 "sg4d_dense_wgrad_partial_floats", "sg4d_frontend_workspace_bytes"]
+                 "sg4d_dense_wgrad_partial_floats", "sg4d_frontend_workspace_bytes", "sg4d_set_compute_precision",
+                 "sg4d_get_compute_precision"]
 
 _lib = None
 
@@ -106,6 +107,8 @@ def load():
         lib.sg4d_colsum_part_doubles.argtypes, lib.sg4d_colsum_part_doubles.restype = [_i64, _i], _i64
         lib.sg4d_dense_wgrad_partial_floats.argtypes, lib.sg4d_dense_wgrad_partial_floats.restype = [_i64, _i, _i], _i64
         lib.sg4d_frontend_workspace_bytes.argtypes, lib.sg4d_frontend_workspace_bytes.restype = [_i, _i, _i], _i64
+        lib.sg4d_set_compute_precision.argtypes, lib.sg4d_set_compute_precision.restype = [_i], _i
+        lib.sg4d_get_compute_precision.argtypes, lib.sg4d_get_compute_precision.restype = [], _i
         if lib.sg4d_abi_version() != 1:
             raise RuntimeError("libsg4d.so ABI version mismatch; rebuild it")
         _lib = lib
@@ -172,6 +175,27 @@ def call(name, ref, *args):
 
 def ptr(t):
     return 0 if t is None else t.data_ptr()
+
+
+class precision:
+    """``with sg4d.precision("bf16"): ...`` -- bf16 operands / fp32 accumulation in every tensor-core layer (BASELINE.json
+    configs[3]; the reference's counterpart is Lightning's ``precision=16`` autocast, SGP/main.py:62-64).  Process-wide."""
+    MODES = {"fp32": 0, "f32": 0, 32: 0, "bf16": 1, 16: 1}
+
+    def __init__(self, mode):
+        self.mode = self.MODES[mode]
+
+    def __enter__(self):
+        self.prev = load().sg4d_get_compute_precision()
+        _check(load().sg4d_set_compute_precision(self.mode), "sg4d_set_compute_precision")
+        return self
+
+    def __exit__(self, *a):
+        load().sg4d_set_compute_precision(self.prev)
+
+
+def set_precision(mode):
+    _check(load().sg4d_set_compute_precision(precision.MODES[mode]), "sg4d_set_compute_precision")
 
 
 def require_cuda(*tensors):

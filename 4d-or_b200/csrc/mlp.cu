@@ -33,6 +33,22 @@
 
 namespace sg4d {
 
+// Process-wide compute precision of the tensor-core layers (sg4d_set_compute_precision):
+//   0  fp32-level: 3xTF32 (4 products in the weight-gradient kernels), the default and the headline configuration
+//   1  bf16: every MMA operand is rounded to bf16 (round to nearest even) when it is staged, ONE product per k-step, fp32
+//      accumulation in TMEM, fp32 BatchNorm statistics / activations in HBM -- BASELINE.json configs[3].  A bf16 value is a
+//      tf32 value, so the same kind::tf32 instruction computes exactly what a bf16 MMA would; what changes is the traffic:
+//      no lo tiles are written or read (shared-memory bytes per k-block drop from 208 KB to 112 KB).
+static int g_precision = 0;
+
+__device__ __forceinline__ float bf16_round(float a) {
+    const uint32_t u = __float_as_uint(a);
+    return __uint_as_float((u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u);      // RNE to 8 exponent + 7 mantissa bits
+}
+__device__ __forceinline__ float4 bf16_round4(const float4 &v) {
+    return make_float4(bf16_round(v.x), bf16_round(v.y), bf16_round(v.z), bf16_round(v.w));
+}
+
 constexpr int kTileM = 128;       // rows per tile = UMMA M
 constexpr int kKB = 32;           // fp32 per k-block (one 128-byte swizzle row)
 constexpr int kStages = 2;
@@ -229,6 +245,7 @@ struct RowGemmArgs {
     int ldg, lde;            // row strides of gsel / garg and of E (0 = N)
     const float *bias;       // EMODE 2: added to every output row (N per panel) or nullptr
     int dbg_no_tma, dbg_no_mma, dbg_no_load, dbg_no_epi;   // ablation switches, honoured only in SG4D_DEBUG builds
+    int lp;                  // 1: bf16 operands, one product per k-step (g_precision)
 };
 
 template <int N>
@@ -330,17 +347,20 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
         auto weights_tma = [&](int stage, int kb) {
             if (tid == 0 && !SG4D_DBG(p.dbg_no_tma)) {   // weight k-block: one bulk-TMA copy (hi tile followed by lo tile)
                 uint8_t *st = smem + stage * SM::kStageBytes;
-                asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * stage),
-                             "r"(2u * SM::kWBytes)
+                const uint32_t wbytes = p.lp ? (uint32_t)SM::kWBytes : 2u * SM::kWBytes;     // bf16 mode: the hi tile only
+                asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * stage), "r"(wbytes)
                              : "memory");
-                tc::bulk_g2s(smem_u32(st + 2 * SM::kABytes), p.wimg + (size_t)kb * (2 * SM::kWBytes / 4), 2u * SM::kWBytes,
-                             bar_full + 8 * stage);
+                tc::bulk_g2s(smem_u32(st + 2 * SM::kABytes), p.wimg + (size_t)kb * (2 * SM::kWBytes / 4), wbytes, bar_full + 8 * stage);
             }
         };
         auto put = [&](uint8_t *st, int r, const float4 &v) {
+            const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+            if (p.lp) {   // bf16 operands: the rounded value IS the operand, no lo tile
+                *reinterpret_cast<float4 *>(st + off) = bf16_round4(v);
+                return;
+            }
             float4 hi, lo;
             split4(v, hi, lo);
-            const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
             *reinterpret_cast<float4 *>(st + off) = hi;
             *reinterpret_cast<float4 *>(st + SM::kABytes + off) = lo;
         };
@@ -502,9 +522,13 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                     for (int ks = 0; ks < kKB / 8 && !SG4D_DBG(p.dbg_no_mma); ++ks) {
                         const uint64_t dah = tc::umma_desc_k_sw128(a_hi + ks * 32), dal = tc::umma_desc_k_sw128(a_lo + ks * 32);
                         const uint64_t dwh = tc::umma_desc_k_sw128(w_hi + ks * 32), dwl = tc::umma_desc_k_sw128(w_lo + ks * 32);
-                        tc::umma_tf32(d_tmem, dal, dwh, idesc, (kb | ks) != 0);   // small terms first
-                        tc::umma_tf32(d_tmem, dah, dwl, idesc, 1u);
-                        tc::umma_tf32(d_tmem, dah, dwh, idesc, 1u);
+                        if (p.lp) {
+                            tc::umma_tf32(d_tmem, dah, dwh, idesc, (kb | ks) != 0);
+                        } else {
+                            tc::umma_tf32(d_tmem, dal, dwh, idesc, (kb | ks) != 0);   // small terms first
+                            tc::umma_tf32(d_tmem, dah, dwl, idesc, 1u);
+                            tc::umma_tf32(d_tmem, dah, dwh, idesc, 1u);
+                        }
                     }
                     tc::umma_commit(bar_empty + 8 * stage);                      // smem stage free when these finish
                     if (kb == nkb - 1) tc::umma_commit(bar_tfull + 8 * acc);     // accumulator ready
@@ -787,6 +811,7 @@ struct WgradArgs {
     // block grid (gridDim.y = mblocks * nnb): CTA (x, y) accumulates the (128 x N) block (y / nnb, y % nnb) of a larger dW
     int nnb, mtot, ktot;
     int dbg_no_mma, dbg_no_load;
+    int lp;                  // 1: bf16 operands, one product per k-step
 };
 
 __device__ __forceinline__ void shift_operand(Operand &o, int c0, int total, int width) {
@@ -970,11 +995,15 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
                         const int item = tid + kProdThreads * i;
                         const int r = item / kPVec, pc4 = item % kPVec;
                         const float4 v = op_apply<PMODE>(p.P, pv[j][i], row_base + r, p.R, 4 * pc4, ps, pt, pp);
-                        float4 hi, lo;
-                        split4_rn(v, hi, lo);
                         const uint32_t off = mn_b32_offset(r, pc4);
-                        *reinterpret_cast<float4 *>(st + off) = hi;
-                        *reinterpret_cast<float4 *>(st + SM::kPBytes + off) = lo;
+                        if (p.lp) {
+                            *reinterpret_cast<float4 *>(st + off) = bf16_round4(v);
+                        } else {
+                            float4 hi, lo;
+                            split4_rn(v, hi, lo);
+                            *reinterpret_cast<float4 *>(st + off) = hi;
+                            *reinterpret_cast<float4 *>(st + SM::kPBytes + off) = lo;
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < kQItems; ++i) {
@@ -995,11 +1024,15 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
                             } else {
                                 v = op_apply<(QMODE == 5 ? 0 : QMODE)>(p.Q, qv[j][i], row_base + r, p.R, 4 * c4, qs, qt, qp);
                             }
-                            float4 hi, lo;
-                            split4_rn(v, hi, lo);
                             const uint32_t off = mn_b32_offset(r, c4);
-                            *reinterpret_cast<float4 *>(st + 2 * SM::kPBytes + off) = hi;
-                            *reinterpret_cast<float4 *>(st + 2 * SM::kPBytes + SM::kQBytes + off) = lo;
+                            if (p.lp) {
+                                *reinterpret_cast<float4 *>(st + 2 * SM::kPBytes + off) = bf16_round4(v);
+                            } else {
+                                float4 hi, lo;
+                                split4_rn(v, hi, lo);
+                                *reinterpret_cast<float4 *>(st + 2 * SM::kPBytes + off) = hi;
+                                *reinterpret_cast<float4 *>(st + 2 * SM::kPBytes + SM::kQBytes + off) = lo;
+                            }
                         }
                     }
                     tc::fence_proxy_async_smem();   // my smem writes -> visible to the tensor core (async proxy)
@@ -1031,10 +1064,14 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
                     const uint32_t ko = ks * p.d_kstep;
                     const uint64_t dph = umma_desc_mn(p_hi + ko, p.d_lbo, p.d_sbo, p.d_type), dpl = umma_desc_mn(p_lo + ko, p.d_lbo, p.d_sbo, p.d_type);
                     const uint64_t dqh = umma_desc_mn(q_hi + ko, p.d_lbo, p.d_sbo, p.d_type), dql = umma_desc_mn(q_lo + ko, p.d_lbo, p.d_sbo, p.d_type);
-                    tc::umma_tf32(d_tmem, dpl, dql, idesc, (pos | ks) != 0);   // 4 products: the tensor pipe has the time,
-                    tc::umma_tf32(d_tmem, dpl, dqh, idesc, 1u);               // and lo*lo is the largest error term left
-                    tc::umma_tf32(d_tmem, dph, dql, idesc, 1u);
-                    tc::umma_tf32(d_tmem, dph, dqh, idesc, 1u);
+                    if (p.lp) {
+                        tc::umma_tf32(d_tmem, dph, dqh, idesc, (pos | ks) != 0);
+                    } else {
+                        tc::umma_tf32(d_tmem, dpl, dql, idesc, (pos | ks) != 0);   // 4 products: the tensor pipe has the time,
+                        tc::umma_tf32(d_tmem, dpl, dqh, idesc, 1u);               // and lo*lo is the largest error term left
+                        tc::umma_tf32(d_tmem, dph, dql, idesc, 1u);
+                        tc::umma_tf32(d_tmem, dph, dqh, idesc, 1u);
+                    }
                 }
                 tc::umma_commit(bar_empty + 8 * stage);
                 if (pos == kRunKb - 1 || kbk == nkb_total - 1) tc::umma_commit(bar_afull + 8 * buf);
@@ -1093,7 +1130,7 @@ wgrad_reduce_kernel(int nparts, int M, int Nv, int N, const float *__restrict__ 
 // ------------------------------------------------------------------------------------------------
 // weight image: W (N, K) fp32 -> [nkb][hi|lo][N rows x 128 B, 128-byte swizzle], zero padded to nkb*32 columns
 __global__ void __launch_bounds__(256)
-pack_weight_kernel(int N, int K, int ldw, const float *__restrict__ W, float *__restrict__ img) {
+pack_weight_kernel(int N, int K, int ldw, const float *__restrict__ W, float *__restrict__ img, int lp) {
     const int nkb = (K + kKB - 1) / kKB;
     const int total = nkb * N * kKB;
     for (int t = blockIdx.x * 256 + threadIdx.x; t < total; t += gridDim.x * 256) {
@@ -1101,7 +1138,8 @@ pack_weight_kernel(int N, int K, int ldw, const float *__restrict__ W, float *__
         const int k = kb * kKB + c;
         const float w = k < K ? W[(size_t)n * ldw + k] : 0.f;
         float hi, lo;
-        tc::split_tf32(w, hi, lo);
+        if (lp) hi = bf16_round(w), lo = 0.f;
+        else tc::split_tf32(w, hi, lo);
         const size_t base = (size_t)kb * (2 * N * kKB);
         const uint32_t off = tc::sw128_offset(n, c) / 4;
         img[base + off] = hi;
@@ -1207,6 +1245,7 @@ static int launch_row(const RowGemmArgs &a0, int grid, cudaStream_t stream, int 
     static const bool no_epi = getenv("SG4D_DBG_NOEPI") != nullptr, no_tma = getenv("SG4D_DBG_NOTMA") != nullptr;
     a.dbg_no_mma = no_mma, a.dbg_no_load = no_load, a.dbg_no_epi = no_epi, a.dbg_no_tma = no_tma;
 #endif
+    a.lp = g_precision;
     auto kern = row_gemm_kernel<N, PM, EM, PT>;
     const int smem = RowSmem<N>::total(PM, EM);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1228,6 +1267,7 @@ static int launch_wgrad(const WgradArgs &a0, int grid, cudaStream_t stream, int 
     static const bool no_mma = getenv("SG4D_DBG_NOMMA") != nullptr, no_load = getenv("SG4D_DBG_NOLOAD") != nullptr;
     a.dbg_no_mma = no_mma, a.dbg_no_load = no_load;
 #endif
+    a.lp = g_precision;
     auto kern = (a.P.ncols <= 64 && blocks == 1) ? wgrad_kernel<N, PM, QM, 64> : wgrad_kernel<N, PM, QM, 128>;
     const int smem = WgSmem<N>::total(PM);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1266,7 +1306,7 @@ extern "C" long long sg4d_weight_image_floats(int n, int k) {
 extern "C" int sg4d_pack_weight(int n, int k, int ldw, const float *w, float *img, sg4d_stream_t stream) {
     if (n <= 0 || k <= 0 || ldw < k || (n & 7) || !w || !img) return SG4D_EINVAL;
     const int total = ((k + kKB - 1) / kKB) * n * kKB;
-    pack_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, k, ldw, w, img);
+    pack_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, k, ldw, w, img, g_precision);
     return SG4D_LAUNCH_CHECK();
 }
 
@@ -1809,6 +1849,7 @@ dense_wgrad_reduce_kernel(int nparts, int mtot, int ktot, int nb_width, int nnb,
 template <int PM, int QM>
 static int launch_dense_wgrad(const WgradArgs &a0, int grid, int blocks, cudaStream_t stream) {
     WgradArgs a = a0;
+    a.lp = g_precision;
     auto kern = wgrad_kernel<128, PM, QM, 128>;
     const int smem = WgSmem<128>::total(PM);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1988,3 +2029,11 @@ extern "C" int sg4d_debug_set_trace(unsigned long long *buf) {
     return status_of(cudaMemcpyToSymbol(sg4d::g_trace, &buf, sizeof(buf)));
 }
 #endif
+
+// Process-wide precision of the tensor-core layers: 0 = fp32-level (3xTF32, default), 1 = bf16 operands / fp32 accumulation.
+extern "C" int sg4d_set_compute_precision(int mode) {
+    if (mode != 0 && mode != 1) return SG4D_EINVAL;
+    sg4d::g_precision = mode;
+    return SG4D_OK;
+}
+extern "C" int sg4d_get_compute_precision(void) { return sg4d::g_precision; }

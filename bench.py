@@ -58,12 +58,14 @@ def parse():
                     help="BASELINE.json configs[config-1]: 1 = 1 scene x 2048 pts forward only; 2 = 8 scenes, encoders only, "
                          "fwd+bwd; 3 = 8 scenes, full pipeline (default, the headline); 4 = 32 scenes + image branch; "
                          "5 = 32 scenes per GPU (256 at 8 GPUs)")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"], help="tensor-core operand precision (config 4: bf16)")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's own code on the GPU")
     ap.add_argument("--e2e-input", default="scene", choices=["scene", "crops", "both"],
                     help="what the end-to-end leg uploads every step: raw scenes (GPU front-end builds the crops) or the crops")
     ap.add_argument("--scene-points", type=int, default=200000, help="points per raw scene of the end-to-end leg")
     a = ap.parse_args()
     a.forward_only, a.encoders_only, a.image = False, False, False
+    a.bf16 = a.config == 4 or a.precision == "bf16"
     if a.config == 1:
         a.scenes_per_gpu, a.points, a.n_obj, a.forward_only = 1, 2048, 4, True
     elif a.config == 2:
@@ -217,10 +219,10 @@ def workload_name(args):
     n_edge = args.n_obj * (args.n_obj - 1) // (2 if args.pairs == "unordered" else 1)
     what = {1: "full pipeline, forward only", 2: "PointNet++ MSG encoders only (upstream gradient = ones), fwd+bwd",
             3: "PointNet++ MSG encoders + TripletGCN + heads, fwd+loss+bwd",
-            4: "full pipeline + image-feature concat branch, fwd+loss+bwd (fp32: the bf16 path is not built)",
+            4: "full pipeline + image-feature concat branch, fwd+loss+bwd, bf16 operands / fp32 accumulation",
             5: "full pipeline, fwd+loss+bwd, scene-sharded data parallel"}[args.config]
     return (f"BASELINE configs[{args.config - 1}]: {args.scenes_per_gpu} scenes/GPU x ({args.n_obj} obj x {args.points} pts + "
-            f"{n_edge} edges x {pr} pts), {what}, fp32")
+            f"{n_edge} edges x {pr} pts), {what}, {'bf16' if args.bf16 else 'fp32'}")
 
 
 def main_reference(args):
@@ -259,6 +261,8 @@ def main_sg4d(args):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
 
+    if args.bf16:
+        _lib.set_precision("bf16")
     cfg = model_config()
     if args.image:
         cfg["IMAGE_INPUT"] = "full"
@@ -629,7 +633,7 @@ def main_sg4d(args):
 
     line = {"metric": "scenes/sec fwd+bwd", "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "bf16" if args.bf16 else "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "scenes_per_gpu": S, "global_scenes": S * world,
                        "parallelism": f"dp{world} (scene-sharded, one grad all-reduce)",
                        "l2": f"inputs are {h2d_bytes / 1e6:.0f} MB per step per GPU (> 126 MB L2), no flush needed",

@@ -404,6 +404,14 @@ int sg4d_frontend_sample(int P, int stride, int clouds, int n, const float *pts,
                          const int *totals, const int64_t *edges, const float *u, float *out, int32_t *picked, float *mean,
                          float *dist, void *scratch, sg4d_stream_t stream);
 
+/* Process-wide compute precision of every tensor-core layer of sections 3-5 (not thread-safe; set it before launching):
+ *   0  fp32-level accuracy: 3xTF32 (default; what the parity bounds and the headline benchmark use)
+ *   1  bf16: operands rounded to bf16 as they are staged, one product per k-step, fp32 accumulation, fp32 statistics and
+ *      activations in memory -- BASELINE.json configs[3]; the reference's counterpart is `precision=16` autocast
+ *      (scene_graph_prediction/main.py:62-64). */
+int sg4d_set_compute_precision(int mode);
+int sg4d_get_compute_precision(void);
+
 #ifdef __cplusplus
 }
 #endif
