@@ -175,6 +175,18 @@ __device__ __forceinline__ float4 sa1_y1bn(const float (&x)[8], const float4 (&w
     }
     return v;
 }
+// same arithmetic, same order, with the weights read from shared memory one input at a time (w: 8 rows of 64 floats, input-major):
+// 4 live weight registers instead of 32 -- the register-starved backward kernels use this form
+__device__ __forceinline__ float4 sa1_y1bn_smem(const float (&x)[8], const float *w, int col, const float4 &t) {
+    float4 v = t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 wj = *reinterpret_cast<const float4 *>(w + j * 64 + col);
+        v.x = __fmaf_rn(x[j], wj.x, v.x), v.y = __fmaf_rn(x[j], wj.y, v.y);
+        v.z = __fmaf_rn(x[j], wj.z, v.z), v.w = __fmaf_rn(x[j], wj.w, v.w);
+    }
+    return v;
+}
 // mode 5: 4 consecutive columns of the grouped row [feats (c, multiple of 4) | xyz - centre | 0-pad]
 __device__ __forceinline__ float4 sa2_gather4(const GroupSrc &g, long long row, bool ok, int col, int i) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -300,15 +312,19 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
     const int K = p.op.ncols;
     const int nkb = (K + kKB - 1) / kKB;
     const long long ntiles = (p.R + kTileM - 1) / kTileM;
-    if (gridDim.y > 1) {   // column panel of a wider layer: shift everything that is indexed by output column
-        const int c0 = blockIdx.y * N;
-        p.wimg += (size_t)blockIdx.y * p.wimg_panel, p.ycol0 += c0;
-        if (p.partial) p.partial += (size_t)blockIdx.y * p.partial_panel;
-        if (p.gamma) p.gamma += c0;
-        if (p.gsel) p.gsel += c0, p.garg += c0;
-        if (p.E) p.E += c0, p.es += c0, p.et += c0, p.ei += c0, p.em += c0;
-        if (p.bias) p.bias += c0;
-    }
+    // column panel of a wider layer (gridDim.y > 1): everything that is indexed by output column is shifted -- in LOCAL
+    // copies; writing to the parameter struct would move all of it to local memory
+    const int c0 = blockIdx.y * N;
+    const float *q_wimg = p.wimg + (size_t)blockIdx.y * p.wimg_panel;
+    const int q_ycol0 = p.ycol0 + c0;
+    double *q_partial = p.partial ? p.partial + (size_t)blockIdx.y * p.partial_panel : nullptr;
+    const float *q_gamma = p.gamma ? p.gamma + c0 : nullptr;
+    float *q_gsel = p.gsel ? p.gsel + c0 : nullptr;
+    uint8_t *q_garg = p.garg ? p.garg + c0 : nullptr;
+    const float *q_E = p.E ? p.E + c0 : nullptr;
+    const float *q_es = p.es ? p.es + c0 : nullptr, *q_et = p.et ? p.et + c0 : nullptr;
+    const float *q_ei = p.ei ? p.ei + c0 : nullptr, *q_em = p.em ? p.em + c0 : nullptr;
+    const float *q_bias = p.bias ? p.bias + c0 : nullptr;
     const int ldg = p.ldg ? p.ldg : N, lde = p.lde ? p.lde : N;
     const uint32_t bar_full = smem_u32(&s_bar[0]), bar_empty = smem_u32(&s_bar[kStages]);
     const uint32_t bar_tfull = smem_u32(&s_bar[2 * kStages]), bar_tempty = smem_u32(&s_bar[2 * kStages + 2]);
@@ -325,6 +341,8 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
         tc::mbar_fence_init();
     }
     if (warp == kProdWarps) tc::tmem_alloc(smem_u32(&s_tmem), 2 * N);
+    if (EMODE == 3)              // s_p[0..511] = W1s for the epilogue's recomputation (PMODE 2 does not use s_p)
+        for (int k = tid; k < 512; k += kMlpThreads) s_p[k] = p.op.g.w1s[k];
     if (PMODE == 4) {            // s_s[0..511] = W1s (input-major, 8 x 64), s_p[0..63] = t1
         for (int k = tid; k < 512; k += kMlpThreads) s_s[k] = p.op.g.w1s[k];
         for (int k = tid; k < 64; k += kMlpThreads) s_p[k] = p.op.g.t1[k];
@@ -332,7 +350,7 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
         for (int k = tid; k < ((K + 31) & ~31); k += kMlpThreads) {
             s_s[k] = k < K ? p.op.s[k] : 0.f;
             s_t[k] = k < K ? p.op.t[k] : 0.f;
-            s_p[k] = (PMODE == 3 && k < K) ? p.op.p[k] : 0.f;
+            if (EMODE != 3) s_p[k] = (PMODE == 3 && k < K) ? p.op.p[k] : 0.f;     // EMODE 3 keeps W1s there
         }
     tc::tc_fence_before_sync();
     __syncthreads();
@@ -350,7 +368,7 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                 const uint32_t wbytes = p.lp ? (uint32_t)SM::kWBytes : 2u * SM::kWBytes;     // bf16 mode: the hi tile only
                 asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * stage), "r"(wbytes)
                              : "memory");
-                tc::bulk_g2s(smem_u32(st + 2 * SM::kABytes), p.wimg + (size_t)kb * (2 * SM::kWBytes / 4), wbytes, bar_full + 8 * stage);
+                tc::bulk_g2s(smem_u32(st + 2 * SM::kABytes), q_wimg + (size_t)kb * (2 * SM::kWBytes / 4), wbytes, bar_full + 8 * stage);
             }
         };
         auto put = [&](uint8_t *st, int r, const float4 &v) {
@@ -435,6 +453,40 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
         RawVec buf[PD][kProdRows];
         long long tile_t = blockIdx.x, tile_i = blockIdx.x;
         int kb_t = 0, kb_i = 0;
+        // Everything that depends only on (thread, tile) is computed once per tile, not once per 16-byte item: the row pointers of
+        // my rows, their validity bits, the shared-memory offsets of my stores (the first version spent ~95 instructions per
+        // float4, two thirds of them 64-bit address arithmetic and bounds predicates; the SM was issue-bound -- DESIGN.md).
+        uint32_t soff[kProdRows];
+#pragma unroll
+        for (int i = 0; i < kProdRows; ++i) {
+            const int r = r0 + (PT / 8) * i;
+            soff[i] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+        }
+        const float *pa[kProdRows], *pa2[kProdRows];
+        const uint8_t *pg[kProdRows];
+        unsigned ok_i = 0, ok_t = 0;
+        auto row_mask = [&](long long tile) {
+            unsigned m = 0;
+#pragma unroll
+            for (int i = 0; i < kProdRows; ++i) m |= (unsigned)(tile < ntiles && tile * kTileM + r0 + (PT / 8) * i < p.R) << i;
+            return m;
+        };
+        auto set_tile_i = [&]() {
+            ok_i = row_mask(tile_i);
+            if constexpr (PMODE != 5) {
+#pragma unroll
+                for (int i = 0; i < kProdRows; ++i) {
+                    const long long row = tile_i * kTileM + r0 + (PT / 8) * i;
+                    pa[i] = p.op.A + row * p.op.lda + 4 * c;
+                    if (PMODE == 3) pa2[i] = p.op.A2 + row * p.op.lda2 + 4 * c;
+                    if (PMODE == 2) {
+                        const long long g = row >> p.op.logS;
+                        pa2[i] = p.op.dsel + g * p.op.ldsel + 4 * c;
+                        pg[i] = p.op.garg + g * p.op.ldsel + 4 * c;
+                    }
+                }
+            }
+        };
         // mode 5 (rows gathered on the fly): the neighbour indices of my rows, for the tile being loaded and the next one
         int ix_cur[kProdRows], ix_nxt[kProdRows];
         auto load_idx = [&](long long tile, int (&dst)[kProdRows]) {
@@ -445,13 +497,23 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
             }
         };
         if (PMODE == 5) load_idx(tile_i, ix_cur), load_idx(tile_i + gridDim.x, ix_nxt);
+        set_tile_i();
+        ok_t = ok_i;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         auto issue = [&](RawVec (&dst)[kProdRows]) {
-            if (tile_i < ntiles && !SG4D_DBG(p.dbg_no_load)) {
+            if (ok_i && !SG4D_DBG(p.dbg_no_load)) {
+                const int off = kb_i * kKB;
+                const bool colv = off + 4 * c < K;
 #pragma unroll
                 for (int i = 0; i < kProdRows; ++i) {
-                    const long long row = tile_i * kTileM + r0 + (PT / 8) * i;
-                    if constexpr (PMODE == 5) dst[i].a = sa2_gather4(p.op.g, row, row < p.R, kb_i * kKB + 4 * c, ix_cur[i]);
-                    else op_load<PMODE>(p.op, row, p.R, kb_i * kKB + 4 * c, dst[i]);
+                    const bool ok = ((ok_i >> i) & 1u) && colv;
+                    if constexpr (PMODE == 5) {
+                        dst[i].a = sa2_gather4(p.op.g, tile_i * kTileM + r0 + (PT / 8) * i, ok, off + 4 * c, ix_cur[i]);
+                    } else {
+                        dst[i].a = ok ? __ldg(reinterpret_cast<const float4 *>(pa[i] + off)) : zero4;
+                        if (PMODE == 3 || PMODE == 2) dst[i].a2 = ok ? __ldg(reinterpret_cast<const float4 *>(pa2[i] + off)) : zero4;
+                        if (PMODE == 2) dst[i].arg = ok ? __ldg(reinterpret_cast<const uint32_t *>(pg[i] + off)) : 0u;
+                    }
                 }
             }
             if (++kb_i == nkb) {
@@ -461,7 +523,29 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                     for (int i = 0; i < kProdRows; ++i) ix_cur[i] = ix_nxt[i];
                     load_idx(tile_i + gridDim.x, ix_nxt);
                 }
+                set_tile_i();
             }
+        };
+        // element transform of one 16-byte item (the prologue of the layer), validity already resolved
+        auto transform = [&](const RawVec &r, bool ok, int rr, int col) -> float4 {
+            if (PMODE == 0 || PMODE == 5) return r.a;                      // invalid items were loaded as zeros
+            if (!ok) return zero4;
+            const float4 sv = *reinterpret_cast<const float4 *>(s_s + col), tv = *reinterpret_cast<const float4 *>(s_t + col);
+            float4 v;
+            v.x = fmaf(r.a.x, sv.x, tv.x), v.y = fmaf(r.a.y, sv.y, tv.y), v.z = fmaf(r.a.z, sv.z, tv.z), v.w = fmaf(r.a.w, sv.w, tv.w);
+            if (PMODE == 1) {
+                v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+            } else if (PMODE == 2) {
+                const uint32_t k = (uint32_t)rr & (uint32_t)(p.op.S - 1);   // 128 % S == 0: the row's slot in its group
+                v.x = (((r.arg) & 0xffu) == k ? r.a2.x : 0.f) - v.x;
+                v.y = (((r.arg >> 8) & 0xffu) == k ? r.a2.y : 0.f) - v.y;
+                v.z = (((r.arg >> 16) & 0xffu) == k ? r.a2.z : 0.f) - v.z;
+                v.w = (((r.arg >> 24) & 0xffu) == k ? r.a2.w : 0.f) - v.w;
+            } else {   // PMODE == 3
+                const float4 pv = *reinterpret_cast<const float4 *>(s_p + col);
+                v.x = fmaf(r.a2.x, pv.x, -v.x), v.y = fmaf(r.a2.y, pv.y, -v.y), v.z = fmaf(r.a2.z, pv.z, -v.z), v.w = fmaf(r.a2.w, pv.w, -v.w);
+            }
+            return v;
         };
 #pragma unroll
         for (int j = 0; j < PD; ++j) issue(buf[j]);
@@ -470,7 +554,6 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
 #pragma unroll
             for (int j = 0; j < PD; ++j) {
                 if (tile_t < ntiles) {
-                    const long long tile = tile_t;
                     const int kb = kb_t;
                     const int stage = (int)(it % kStages);
                     SG4D_TRACE(tid == 0 && it < 400, it * 5);
@@ -479,10 +562,18 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                     uint8_t *st = smem + stage * SM::kStageBytes;
                     weights_tma(stage, kb);
                     const int col = kb * kKB + 4 * c;
+                    const bool colv = col < K;
 #pragma unroll
                     for (int i = 0; i < kProdRows; ++i) {
-                        const int r = r0 + (PT / 8) * i;
-                        put(st, r, op_apply<(PMODE == 5 ? 0 : PMODE)>(p.op, buf[j][i], tile * kTileM + r, p.R, col, s_s, s_t, s_p));
+                        const float4 v = transform(buf[j][i], ((ok_t >> i) & 1u) && colv, r0 + (PT / 8) * i, col);
+                        if (p.lp) {   // bf16 operands: the rounded value IS the operand, no lo tile
+                            *reinterpret_cast<float4 *>(st + soff[i]) = bf16_round4(v);
+                        } else {
+                            float4 hi, lo;
+                            split4(v, hi, lo);
+                            *reinterpret_cast<float4 *>(st + soff[i]) = hi;
+                            *reinterpret_cast<float4 *>(st + SM::kABytes + soff[i]) = lo;
+                        }
                     }
                     SG4D_TRACE(tid == 0 && it < 400, it * 5 + 2);
                     tc::fence_proxy_async_smem();   // my smem writes -> visible to the tensor core (async proxy)
@@ -491,7 +582,10 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                     if (lane == 0) tc::mbar_arrive(bar_full + 8 * stage);
                     SG4D_TRACE(tid == 0 && it < 400, it * 5 + 4);
                     issue(buf[j]);   // refill this ring slot
-                    if (++kb_t == nkb) kb_t = 0, tile_t += gridDim.x;
+                    if (++kb_t == nkb) {
+                        kb_t = 0, tile_t += gridDim.x;
+                        ok_t = row_mask(tile_t);
+                    }
                     ++it;
                 }
             }
@@ -549,18 +643,16 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
         const int rbeg = (e / N) * (kTileM / (kEpiThreads / N));
         const int rcnt = kTileM / (kEpiThreads / N);
         bool want_max = true;
-        if (EMODE == 0 && p.S > 0) want_max = __ldg(p.gamma + col) >= 0.f;
+        if (EMODE == 0 && p.S > 0) want_max = __ldg(q_gamma + col) >= 0.f;
         double dacc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         // EMODE 3: thread (cg, rs) owns channels 4cg..4cg+3 and rows 16rs..16rs+15 of every tile
         float *xa_s = reinterpret_cast<float *>(smem + kStages * SM::kStageBytes + SM::kCBytes + SM::kConst);
         double *sacc = reinterpret_cast<double *>(smem + kStages * SM::kStageBytes + SM::kCBytes + SM::kConst + SM::kXaBytes);
         const int cg = e & 15, rs = e >> 4;
-        float4 w1[8], t1v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 t1v = make_float4(0.f, 0.f, 0.f, 0.f);
         float sa[32];
         int since = 0, ixn = 0;
-        if constexpr (EMODE == 3) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) w1[j] = __ldg(reinterpret_cast<const float4 *>(p.op.g.w1s + j * 64 + 4 * cg));
+        if constexpr (EMODE == 3) {   // W1s was staged into s_p (free in PMODE 2) before the role split
             t1v = __ldg(reinterpret_cast<const float4 *>(p.op.g.t1 + 4 * cg));
 #pragma unroll
             for (int u = 0; u < 32; ++u) sa[u] = 0.f, sacc[u * kEpiThreads + e] = 0.0;
@@ -633,7 +725,7 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                     const float4 xa0 = *reinterpret_cast<const float4 *>(xa_s + r * 8), xa1 = *reinterpret_cast<const float4 *>(xa_s + r * 8 + 4);
                     const float xa[8] = {xa0.x, xa0.y, xa0.z, xa0.w, xa1.x, xa1.y, xa1.z, xa1.w};
                     float4 d = *reinterpret_cast<const float4 *>(Cs + r * SM::kCStride + 4 * cg);
-                    const float4 y = sa1_y1bn(xa, w1, t1v);
+                    const float4 y = sa1_y1bn_smem(xa, s_p, 4 * cg, t1v);
                     d.x = y.x > 0.f ? d.x : 0.f, d.y = y.y > 0.f ? d.y : 0.f, d.z = y.z > 0.f ? d.z : 0.f, d.w = y.w > 0.f ? d.w : 0.f;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -650,15 +742,15 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                 // ReLU mask of the inner layer from its pre-activation E (one coalesced read of E), store of dz,
                 // and the two BatchNorm-backward reductions -- every thread owns 4 fixed columns in this pass
                 const int cc = (e % kVecPerRow) * 4;
-                const float4 sv = __ldg(reinterpret_cast<const float4 *>(p.es + cc)), tv = __ldg(reinterpret_cast<const float4 *>(p.et + cc));
-                const float4 iv = __ldg(reinterpret_cast<const float4 *>(p.ei + cc)), mv = __ldg(reinterpret_cast<const float4 *>(p.em + cc));
+                const float4 sv = __ldg(reinterpret_cast<const float4 *>(q_es + cc)), tv = __ldg(reinterpret_cast<const float4 *>(q_et + cc));
+                const float4 iv = __ldg(reinterpret_cast<const float4 *>(q_ei + cc)), mv = __ldg(reinterpret_cast<const float4 *>(q_em + cc));
                 float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
                 for (int rb = e / kVecPerRow; rb < nvalid; rb += 4 * kRowStep) {
                     float4 ev[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int r = rb + u * kRowStep;
-                        ev[u] = r < nvalid ? __ldg(reinterpret_cast<const float4 *>(p.E + (row0 + r) * lde + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        ev[u] = r < nvalid ? __ldg(reinterpret_cast<const float4 *>(q_E + (row0 + r) * lde + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -669,7 +761,7 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                             dv.y = fmaf(ev[u].y, sv.y, tv.y) > 0.f ? dv.y : 0.f;
                             dv.z = fmaf(ev[u].z, sv.z, tv.z) > 0.f ? dv.z : 0.f;
                             dv.w = fmaf(ev[u].w, sv.w, tv.w) > 0.f ? dv.w : 0.f;
-                            *reinterpret_cast<float4 *>(p.Y + (row0 + r) * p.ldy + p.ycol0 + cc) = dv;
+                            *reinterpret_cast<float4 *>(p.Y + (row0 + r) * p.ldy + q_ycol0 + cc) = dv;
                             a0.x += dv.x, a0.y += dv.y, a0.z += dv.z, a0.w += dv.w;
                             a1.x = fmaf(dv.x, fmaf(ev[u].x, iv.x, mv.x), a1.x);
                             a1.y = fmaf(dv.y, fmaf(ev[u].y, iv.y, mv.y), a1.y);
@@ -682,12 +774,12 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                 dacc[4] += a1.x, dacc[5] += a1.y, dacc[6] += a1.z, dacc[7] += a1.w;
             } else if (p.Y) {   // coalesced store of the tile: 16 bytes per thread per step
                 float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (EMODE == 2 && p.bias) bv = __ldg(reinterpret_cast<const float4 *>(p.bias + (e % kVecPerRow) * 4));   // kEpiThreads % kVecPerRow == 0: my columns are fixed
+                if (EMODE == 2 && q_bias) bv = __ldg(reinterpret_cast<const float4 *>(q_bias + (e % kVecPerRow) * 4));   // kEpiThreads % kVecPerRow == 0: my columns are fixed
                 for (int v4 = e; v4 < nvalid * kVecPerRow; v4 += kEpiThreads) {
                     const int r = v4 / kVecPerRow, cc = (v4 % kVecPerRow) * 4;
                     float4 v = *reinterpret_cast<const float4 *>(Cs + r * SM::kCStride + cc);
                     if (EMODE == 2) v.x += bv.x, v.y += bv.y, v.z += bv.z, v.w += bv.w;
-                    *reinterpret_cast<float4 *>(p.Y + (row0 + r) * p.ldy + p.ycol0 + cc) = v;
+                    *reinterpret_cast<float4 *>(p.Y + (row0 + r) * p.ldy + q_ycol0 + cc) = v;
                 }
             }
             SG4D_TRACE(e == 0 && ti < 256, 5120 + (int)ti * 5 + 3);
@@ -727,8 +819,8 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                             bi = take ? k0 + ix[0] : bi;
                             if (((r + 8) & smask) == 0) {             // last batch of the group (warp-uniform)
                                 const long long g = (row0 + r) >> p.logS;
-                                p.gsel[g * ldg + col] = best * sgn;
-                                p.garg[g * ldg + col] = (uint8_t)bi;
+                                q_gsel[g * ldg + col] = best * sgn;
+                                q_garg[g * ldg + col] = (uint8_t)bi;
                             }
                         }
                     }
@@ -747,8 +839,8 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                             bi = better ? k : bi;
                             if (k == smask) {
                                 const long long g = (row0 + r) >> p.logS;
-                                p.gsel[g * ldg + col] = best;
-                                p.garg[g * ldg + col] = (uint8_t)bi;
+                                q_gsel[g * ldg + col] = best;
+                                q_garg[g * ldg + col] = (uint8_t)bi;
                             }
                         }
                     }
@@ -772,8 +864,8 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                 }
             }
         } else if (EMODE == 0) {
-            p.partial[((size_t)blockIdx.x * kEpiThreads + e) * 2 + 0] = dacc[0];
-            p.partial[((size_t)blockIdx.x * kEpiThreads + e) * 2 + 1] = dacc[1];
+            q_partial[((size_t)blockIdx.x * kEpiThreads + e) * 2 + 0] = dacc[0];
+            q_partial[((size_t)blockIdx.x * kEpiThreads + e) * 2 + 1] = dacc[1];
         } else if (EMODE == 1) {
             // fold the per-thread (4 columns x 2) fp64 sums into one pair per column, in a fixed order
             constexpr int kVecPerRow = N / 4;
@@ -788,8 +880,8 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
                     t0 += sd[t * 8 + (e & 3)], t1 += sd[t * 8 + 4 + (e & 3)];
                 }
             }
-            p.partial[((size_t)blockIdx.x * kEpiThreads + e) * 2 + 0] = t0;
-            p.partial[((size_t)blockIdx.x * kEpiThreads + e) * 2 + 1] = t1;
+            q_partial[((size_t)blockIdx.x * kEpiThreads + e) * 2 + 0] = t0;
+            q_partial[((size_t)blockIdx.x * kEpiThreads + e) * 2 + 1] = t1;
         }
     }
     tc::tc_fence_before_sync();
@@ -856,8 +948,10 @@ struct WgSmem {
 
 // MV = valid channels of P (64 or 128): with 64 the upper half of the P tiles is zeroed once and never rewritten, so
 // the producers only transform the 16 valid float4 columns of each row
-template <int N, int PMODE, int QMODE, int MV>
+template <int N, int PMODE, int QMODE, int MV, bool LP = false>
 __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
+    // (registers are allocated per 4 warps: 21 warps count as 24, which caps this kernel at 80 registers per thread -- the
+    //  bf16 variant is a separate instantiation so that its branches do not add to the pressure of the fp32 one)
     constexpr int kProdThreads = kProdThreadsT2, kProdWarps = kProdThreads / 32, kMlpThreads = kMlpThreadsT2;
     using SM = WgSmem<N>;
     constexpr int kStages = SM::stages(PMODE);
@@ -876,11 +970,15 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // (block of a larger dW: operands shifted in LOCAL copies -- writing to the parameter struct would move it to local memory
+    //  and turn every p.* access of the hot loops into a local load)
+    Operand OP = p.P, OQ = p.Q;
+    float *partial_out = p.partial;
     if (gridDim.y > 1) {
         const int mb = blockIdx.y / p.nnb, nb = blockIdx.y % p.nnb;
-        shift_operand(p.P, mb * kTileM, p.mtot, kTileM);
-        shift_operand(p.Q, nb * N, p.ktot, N);
-        p.partial += (size_t)blockIdx.y * gridDim.x * kTileM * N;
+        shift_operand(OP, mb * kTileM, p.mtot, kTileM);
+        shift_operand(OQ, nb * N, p.ktot, N);
+        partial_out += (size_t)blockIdx.y * gridDim.x * kTileM * N;
     }
     const long long ntiles = (p.R + kTileM - 1) / kTileM;
     const long long per = (ntiles + gridDim.x - 1) / gridDim.x;
@@ -902,15 +1000,15 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
     }
     if (warp == kProdWarps) tc::tmem_alloc(smem_u32(&s_tmem), 2 * kTmemCols);
     for (int k = tid; k < 256; k += kMlpThreads) {
-        ps[k] = (PMODE != 0 && k < p.P.ncols) ? p.P.s[k] : 0.f;
-        pt[k] = (PMODE != 0 && k < p.P.ncols) ? p.P.t[k] : 0.f;
-        pp[k] = (PMODE == 3 && k < p.P.ncols) ? p.P.p[k] : 0.f;
+        ps[k] = (PMODE != 0 && k < OP.ncols) ? OP.s[k] : 0.f;
+        pt[k] = (PMODE != 0 && k < OP.ncols) ? OP.t[k] : 0.f;
+        pp[k] = (PMODE == 3 && k < OP.ncols) ? OP.p[k] : 0.f;
         if (QMODE == 4) {      // qs[0..511] (= qs | qt) = W1s (input-major, 8 x 64), qp[0..63] = t1
-            qs[k] = p.Q.g.w1s[k], qt[k] = p.Q.g.w1s[256 + k];
-            qp[k] = k < 64 ? p.Q.g.t1[k] : 0.f;
+            qs[k] = OQ.g.w1s[k], qt[k] = OQ.g.w1s[256 + k];
+            qp[k] = k < 64 ? OQ.g.t1[k] : 0.f;
         } else {
-            qs[k] = (QMODE == 1 && k < p.Q.ncols) ? p.Q.s[k] : 0.f;
-            qt[k] = (QMODE == 1 && k < p.Q.ncols) ? p.Q.t[k] : 0.f;
+            qs[k] = (QMODE == 1 && k < OQ.ncols) ? OQ.s[k] : 0.f;
+            qt[k] = (QMODE == 1 && k < OQ.ncols) ? OQ.t[k] : 0.f;
             qp[k] = 0.f;
         }
     }
@@ -941,7 +1039,7 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
         auto q_row_idx = [&](long long kbk, int i) -> uint32_t {
             const int item = tid + kProdThreads * i;
             const long long row = t_beg * kTileM + kbk * kKB + item / kQVec;
-            return (kbk < nkb_total && item < 32 * kQVec && row < p.R) ? (uint32_t)__ldg(p.Q.g.idx + row) : 0u;
+            return (kbk < nkb_total && item < 32 * kQVec && row < p.R) ? (uint32_t)__ldg(OQ.g.idx + row) : 0u;
         };
         auto issue = [&](long long kbk, RawVec (&pd)[kPItems], RawVec (&qd)[kQItems]) {
             if (kbk < nkb_total && !SG4D_DBG(p.dbg_no_load)) {
@@ -949,7 +1047,7 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
 #pragma unroll
                 for (int i = 0; i < kPItems; ++i) {
                     const int item = tid + kProdThreads * i;
-                    op_load<PMODE>(p.P, row_base + item / kPVec, p.R, 4 * (item % kPVec), pd[i]);
+                    op_load<PMODE>(OP, row_base + item / kPVec, p.R, 4 * (item % kPVec), pd[i]);
                 }
 #pragma unroll
                 for (int i = 0; i < kQItems; ++i) {
@@ -958,12 +1056,12 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
                     if (item < 32 * kQVec) {
                         if constexpr (QMODE == 4) {
                             float x[8];
-                            sa1_gather_row(p.Q.g, row_base + r, row_base + r < p.R, (int)qd[i].arg, x);
+                            sa1_gather_row(OQ.g, row_base + r, row_base + r < p.R, (int)qd[i].arg, x);
                             qd[i].a = make_float4(x[0], x[1], x[2], x[3]), qd[i].a2 = make_float4(x[4], x[5], x[6], x[7]);
                         } else if constexpr (QMODE == 5) {
-                            qd[i].a = sa2_gather4(p.Q.g, row_base + r, row_base + r < p.R, 4 * c4, (int)qd[i].arg);
+                            qd[i].a = sa2_gather4(OQ.g, row_base + r, row_base + r < p.R, 4 * c4, (int)qd[i].arg);
                         } else {
-                            op_load<QMODE>(p.Q, row_base + r, p.R, 4 * c4, qd[i]);
+                            op_load<QMODE>(OQ, row_base + r, p.R, 4 * c4, qd[i]);
                         }
                     }
                 }
@@ -994,9 +1092,9 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
                     for (int i = 0; i < kPItems; ++i) {
                         const int item = tid + kProdThreads * i;
                         const int r = item / kPVec, pc4 = item % kPVec;
-                        const float4 v = op_apply<PMODE>(p.P, pv[j][i], row_base + r, p.R, 4 * pc4, ps, pt, pp);
+                        const float4 v = op_apply<PMODE>(OP, pv[j][i], row_base + r, p.R, 4 * pc4, ps, pt, pp);
                         const uint32_t off = mn_b32_offset(r, pc4);
-                        if (p.lp) {
+                        if constexpr (LP) {
                             *reinterpret_cast<float4 *>(st + off) = bf16_round4(v);
                         } else {
                             float4 hi, lo;
@@ -1014,18 +1112,15 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
                             if constexpr (QMODE == 4) {     // relu(W1s x + t1), the second layer's input, recomputed
                                 const float x[8] = {qv[j][i].a.x, qv[j][i].a.y, qv[j][i].a.z, qv[j][i].a.w,
                                                     qv[j][i].a2.x, qv[j][i].a2.y, qv[j][i].a2.z, qv[j][i].a2.w};
-                                float4 w[8];
-#pragma unroll
-                                for (int u = 0; u < 8; ++u) w[u] = *reinterpret_cast<const float4 *>(qs + u * 64 + 4 * c4);
-                                v = sa1_y1bn(x, w, *reinterpret_cast<const float4 *>(qp + 4 * c4));
+                                v = sa1_y1bn_smem(x, qs, 4 * c4, *reinterpret_cast<const float4 *>(qp + 4 * c4));
                                 const bool ok = row_base + r < p.R;
                                 v.x = ok ? fmaxf(v.x, 0.f) : 0.f, v.y = ok ? fmaxf(v.y, 0.f) : 0.f;
                                 v.z = ok ? fmaxf(v.z, 0.f) : 0.f, v.w = ok ? fmaxf(v.w, 0.f) : 0.f;
                             } else {
-                                v = op_apply<(QMODE == 5 ? 0 : QMODE)>(p.Q, qv[j][i], row_base + r, p.R, 4 * c4, qs, qt, qp);
+                                v = op_apply<(QMODE == 5 ? 0 : QMODE)>(OQ, qv[j][i], row_base + r, p.R, 4 * c4, qs, qt, qp);
                             }
                             const uint32_t off = mn_b32_offset(r, c4);
-                            if (p.lp) {
+                            if constexpr (LP) {
                                 *reinterpret_cast<float4 *>(st + 2 * SM::kPBytes + off) = bf16_round4(v);
                             } else {
                                 float4 hi, lo;
@@ -1064,7 +1159,7 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
                     const uint32_t ko = ks * p.d_kstep;
                     const uint64_t dph = umma_desc_mn(p_hi + ko, p.d_lbo, p.d_sbo, p.d_type), dpl = umma_desc_mn(p_lo + ko, p.d_lbo, p.d_sbo, p.d_type);
                     const uint64_t dqh = umma_desc_mn(q_hi + ko, p.d_lbo, p.d_sbo, p.d_type), dql = umma_desc_mn(q_lo + ko, p.d_lbo, p.d_sbo, p.d_type);
-                    if (p.lp) {
+                    if constexpr (LP) {
                         tc::umma_tf32(d_tmem, dph, dqh, idesc, (pos | ks) != 0);
                     } else {
                         tc::umma_tf32(d_tmem, dpl, dql, idesc, (pos | ks) != 0);   // 4 products: the tensor pipe has the time,
@@ -1081,7 +1176,7 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
     } else {
         // epilogue: after every run, partial (128 x N) of this CTA (+)= the run's accumulator (zeros when it had no tile)
         const int q = warp & 3, row = q * 32 + lane;
-        float *out = p.partial + ((size_t)blockIdx.x * kTileM + row) * N;
+        float *out = partial_out + ((size_t)blockIdx.x * kTileM + row) * N;
         const long long nruns = (nkb_total + kRunKb - 1) / kRunKb;
         for (long long run = 0; run < nruns; ++run) {
             const int buf = (int)(run & 1);
@@ -1268,7 +1363,8 @@ static int launch_wgrad(const WgradArgs &a0, int grid, cudaStream_t stream, int 
     a.dbg_no_mma = no_mma, a.dbg_no_load = no_load;
 #endif
     a.lp = g_precision;
-    auto kern = (a.P.ncols <= 64 && blocks == 1) ? wgrad_kernel<N, PM, QM, 64> : wgrad_kernel<N, PM, QM, 128>;
+    auto kern = (a.P.ncols <= 64 && blocks == 1) ? (a.lp ? wgrad_kernel<N, PM, QM, 64, true> : wgrad_kernel<N, PM, QM, 64, false>)
+                                                  : (a.lp ? wgrad_kernel<N, PM, QM, 128, true> : wgrad_kernel<N, PM, QM, 128, false>);
     const int smem = WgSmem<N>::total(PM);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return status_of(e);
@@ -1850,7 +1946,7 @@ template <int PM, int QM>
 static int launch_dense_wgrad(const WgradArgs &a0, int grid, int blocks, cudaStream_t stream) {
     WgradArgs a = a0;
     a.lp = g_precision;
-    auto kern = wgrad_kernel<128, PM, QM, 128>;
+    auto kern = a.lp ? wgrad_kernel<128, PM, QM, 128, true> : wgrad_kernel<128, PM, QM, 128, false>;
     const int smem = WgSmem<128>::total(PM);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return status_of(e);
