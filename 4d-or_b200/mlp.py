@@ -263,7 +263,7 @@ class _FusedSA1(torch.autograd.Function):
                   part2.data_ptr(), g2.data_ptr(), gsel.data_ptr(), garg.data_ptr())
         s2, t2, m2, i2 = bn_scale_shift(bn2, part2, rows)
         out = torch.relu(torch.addcmul(t2, gsel, s2))
-        _capture(kind="sa1", garg=garg, gsel=gsel, y2=y2, stats1=stats1, moments=moments, w1s=w1s)
+        _capture(kind="sa1", garg=garg, gsel=gsel, y2=y2, stats1=stats1, moments=moments, w1s=w1s, out=out)
         ctx.save_for_backward(pts, feats, centers, idx, y2, gsel, garg, out, w1, w2, stats1, w1s, moments, s2, m2, i2)
         ctx.meta = (foff, c, batch1, bn2.training or not bn2.track_running_stats)
         return out
@@ -310,7 +310,7 @@ class _FusedSA2(torch.autograd.Function):
         y2, part2, gsel, garg = linear_fwd(y1, n1, pack_weight(w2), n2, scale=s1, shift=t1, group=ns, gamma=g2)
         s2, t2, m2, i2 = bn_scale_shift(bn2, part2, rows)
         out = torch.relu(torch.addcmul(t2, gsel, s2))
-        _capture(kind="sa2", garg=garg, gsel=gsel, y1=y1, y2=y2, s1=s1, t1=t1)
+        _capture(kind="sa2", garg=garg, gsel=gsel, y1=y1, y2=y2, s1=s1, t1=t1, out=out)
         ctx.save_for_backward(pts, feats, centers, idx, cnt, y1, y2, gsel, garg, out, w1g, w2, s1, t1, m1, i1, s2, m2, i2)
         ctx.meta = (foff, c, bn1.training or not bn1.track_running_stats, bn2.training or not bn2.track_running_stats)
         return out

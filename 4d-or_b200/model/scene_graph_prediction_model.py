@@ -106,9 +106,20 @@ class SGPNModelWrapper(nn.Module):
         return obj_cls, rel_cls
 
     # ------------------------------------------------------------------ steps (reference :134-177)
+    def _class_weights(self, device):
+        """the class-weight vectors on `device`, uploaded once (the reference re-uploads them every step, :139-140; a copy
+        from pageable host memory can also not be captured into a CUDA graph)"""
+        cache = self.__dict__.setdefault('_weights_on', {})
+        key = (str(device), id(self.weights_obj), id(self.weights_rel))
+        if key not in cache:
+            cache.clear()
+            cache[key] = (self.weights_obj.to(device), self.weights_rel.to(device))
+        return cache[key]
+
     def loss(self, obj_pred, rel_pred, batch):
-        loss_obj = F.nll_loss(obj_pred, batch['gt_class'], weight=self.weights_obj.to(obj_pred.device))
-        loss_rel = F.nll_loss(rel_pred, batch['gt_rels'], weight=self.weights_rel.to(rel_pred.device))
+        w_obj, w_rel = self._class_weights(obj_pred.device)
+        loss_obj = F.nll_loss(obj_pred, batch['gt_class'], weight=w_obj)
+        loss_rel = F.nll_loss(rel_pred, batch['gt_rels'], weight=w_rel)
         return self.mconfig['lambda_o'] * loss_obj + loss_rel
 
     # per-take relation predictions for the epoch metrics (reference :113-132); set by the trainer (sg4d.metrics.RelationMetrics)

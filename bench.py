@@ -59,6 +59,7 @@ def parse():
                          "fwd+bwd; 3 = 8 scenes, full pipeline (default, the headline); 4 = 32 scenes + image branch; "
                          "5 = 32 scenes per GPU (256 at 8 GPUs)")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"], help="tensor-core operand precision (config 4: bf16)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying its CUDA graph")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's own code on the GPU")
     ap.add_argument("--e2e-input", default="scene", choices=["scene", "crops", "both"],
                     help="what the end-to-end leg uploads every step: raw scenes (GPU front-end builds the crops) or the crops")
@@ -307,6 +308,29 @@ def main_sg4d(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    eager_step = step
+    graphed = None
+    if not args.no_graph:
+        # the whole forward + loss + backward is captured once and replayed: one graph launch per step instead of ~800 launches
+        from sg4d import graph as sg_graph
+
+        def body(b):
+            if args.forward_only:
+                with torch.no_grad():
+                    return model.training_step(b)
+            if args.encoders_only:
+                obj_f, rel_f = model._encode(b)
+                return obj_f.sum() + rel_f.sum()
+            return model.training_step(b)
+
+        graphed = sg_graph.GraphedStep(model, resident, bucket, step_fn=body)
+
+        def step(batch):
+            loss = graphed(batch)
+            if not args.forward_only:
+                bucket.all_reduce_mean()
+            return loss
+
     for _ in range(args.warmup):
         step(resident)
     barrier()
@@ -334,10 +358,13 @@ def main_sg4d(args):
     _lib.drain_timing()
     barrier()
     kt0, kt1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lc0 = _lib.LAUNCH_COUNT
     kt0.record()
     for i in range(args.steps):
-        step(resident)
+        eager_step(resident)
     kt1.record()
+    if graphed is not None:      # a replayed graph launches the same kernels as the eager step it was captured from
+        launches = _lib.LAUNCH_COUNT - lc0
     barrier()
     per_call = _lib.drain_timing()
     _lib.enable_timing(False)
@@ -638,6 +665,7 @@ def main_sg4d(args):
                        "parallelism": f"dp{world} (scene-sharded, one grad all-reduce)",
                        "l2": f"inputs are {h2d_bytes / 1e6:.0f} MB per step per GPU (> 126 MB L2), no flush needed",
                        "peak_memory_gb": round(peak_mem_gb, 2),
+                       "launch": "eager" if args.no_graph else "one CUDA-graph replay per step (capture of the eager step)",
                        "cpu_sample": cpu["sample"] if cpu else None},
             "clocks": clk.summary(), "e2e": e2e, "e2e_crops": e2e_crops, "gpu_launches": launches,
             "roofline": roof, "cpu_baseline": cpu, "gpu_reference": gpu_ref,

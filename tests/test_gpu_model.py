@@ -99,7 +99,39 @@ def test_model_against_reference_fixture(cuda, golden_dir):
     np.testing.assert_allclose(eo[1].cpu().numpy(), fx["eval_rel_cls"], rtol=0, atol=max(1e-4, 10 * out_floor["rel_cls"]))
 
 
-def _oracle_run(sd, batch, lambda_o, image=False, w_obj=None, w_rel=None, jitter_seed=None):
+def _pins_from_captures(caps):
+    """sg4d's selections (max-pool rows, the two ReLU active sets) of every set-abstraction scale, in the oracle's
+    channel-major layout and keyed by the oracle's module prefixes.  Capture order = call order: the object encoder's five
+    scales (SA1 x 2, SA2 x 2, SA3), then the edge encoder's."""
+    import sa_ref
+    pins, scales, inputs = {}, [], None
+    for q in caps:
+        if "mlp" in q:
+            inputs = q
+        elif "garg" in q:
+            scales.append((inputs if q["kind"] in ("sa1", "sa2") else None, q))
+            inputs = None
+    assert len(scales) == 10, len(scales)
+    names = [(enc, lvl, sc) for enc in ("obj_encoder", "rel_encoder") for lvl, sc in ((0, 0), (0, 1), (1, 0), (1, 1), (2, 0))]
+    for (enc, lvl, sc), (inp, q) in zip(names, scales):
+        g, c2 = q["garg"].shape
+        if inp is not None:
+            b, m, ns = inp["idx"].shape
+            x32 = sa_ref.grouped_fp64(inp["pts"], inp["feats"] if inp["feats"] is not None else inp["pts"], inp["foff"], inp["c"],
+                                      inp["centers"], inp["idx"]).float()
+            h1 = sa_ref.h1_mask(q, x32)
+        else:                                   # SA3 (GroupAll): one group of n points per cloud
+            h1 = sa_ref.h1_mask(q, None)
+            b, m, ns = g, 1, h1.shape[0] // g
+        c2 = q["out"].shape[1]
+        pins[f"{enc}.backbone.SA_modules.{lvl}.{sc}"] = (
+            h1.view(b, m, ns, -1).permute(0, 3, 1, 2).float().cpu(),
+            q["garg"][:, :c2].view(b, m, c2).permute(0, 2, 1).unsqueeze(-1).long().cpu(),
+            (q["out"] > 0).view(b, m, c2).permute(0, 2, 1).float().cpu())
+    return pins
+
+
+def _oracle_run(sd, batch, lambda_o, image=False, w_obj=None, w_rel=None, jitter_seed=None, pins=None):
     s = model_ref.clone_state(sd)
     if jitter_seed is not None:      # 1e-7 relative weight noise = the scale of fp32 rounding
         g = torch.Generator().manual_seed(jitter_seed)
@@ -107,7 +139,7 @@ def _oracle_run(sd, batch, lambda_o, image=False, w_obj=None, w_rel=None, jitter
             for k, v in s.items():
                 if v.is_floating_point() and "running" not in k:
                     v.mul_(1 + 1e-7 * torch.randn(v.shape, generator=g))
-    outs = model_ref.forward(s, batch, training=True, dropout=False, image=image)
+    outs = model_ref.forward(s, batch, training=True, dropout=False, image=image, pins=pins)
     loss = model_ref.loss_fn(outs[0], outs[1], batch, torch.ones(12) if w_obj is None else w_obj,
                              torch.ones(15) if w_rel is None else w_rel, lambda_o)
     loss.backward()
@@ -117,7 +149,7 @@ def _oracle_run(sd, batch, lambda_o, image=False, w_obj=None, w_rel=None, jitter
 OUT_NAMES = ("obj_cls", "rel_cls", "obj_feature", "rel_feature", "gcn_obj", "gcn_rel")
 
 
-def _noise_floor(sd, batch, lambda_o, ref, image=False, **kw):
+def _noise_floor(sd, batch, lambda_o, ref, image=False, pins=None, **kw):
     """How far the ORACLE's own outputs / gradients move under 1e-7 relative weight noise.  The GCN's
     BatchNorm1d layers normalise over only n_obj / n_edge rows, which amplifies fp32 rounding by orders of
     magnitude for small scenes; a fixed 1e-4 bound is below that floor there.  Tolerances below are
@@ -126,7 +158,7 @@ def _noise_floor(sd, batch, lambda_o, ref, image=False, **kw):
     out_floor = {n: 0.0 for n in OUT_NAMES}
     grad_floor = {}
     for seed in (1, 2):
-        s, o, _ = _oracle_run(sd, batch, lambda_o, image, jitter_seed=seed, **kw)
+        s, o, _ = _oracle_run(sd, batch, lambda_o, image, jitter_seed=seed, pins=pins, **kw)
         for n, a, b in zip(OUT_NAMES, o, o0):
             out_floor[n] = max(out_floor[n], float((a - b).abs().max()))
         for k, v in s.items():
@@ -136,17 +168,17 @@ def _noise_floor(sd, batch, lambda_o, ref, image=False, **kw):
 
 
 def _assert_grad_close(name, got, ref, floor):
-    """Gradients are piecewise smooth: an arg-max of the max-pool flipping between two near-tied rows (a
-    1e-7 effect in the forward pass) re-routes one channel's gradient, so an element-wise bound cannot hold
-    for 100 % of the entries.  Required: relative L2 error <= 2e-3 (or 10x the oracle's own jitter response)
-    and >= 98 % of the entries within the element-wise tolerance."""
+    """Gradient parity with the set-abstraction selections PINNED to sg4d's (max-pool rows, ReLU active sets fed to the
+    oracle): the gradient is then a smooth function of the inputs, so EVERY entry must be within the tolerance -- 1e-4 of the
+    largest entry, or 10x the oracle's own response to 1e-7 weight noise where the GCN's BatchNorm1d over a handful of rows
+    makes the problem ill-conditioned (_noise_floor) -- and the relative L2 error within 1e-4 (or that floor)."""
     scale = max(1.0, float(ref.abs().max()))
-    tol = max(2e-4 * scale, 10 * floor)
+    tol = max(1e-4 * scale, 10 * floor)
     diff = (got - ref).abs()
-    frac_bad = float((diff > tol).float().mean())
+    worst = float(diff.max())
     rel_l2 = float(diff.double().norm() / max(1e-12, float(ref.double().norm())))
-    l2_tol = max(2e-3, 10 * floor * ref.numel() ** 0.5 / max(1e-12, float(ref.double().norm())))
-    assert frac_bad <= 0.02 and rel_l2 <= l2_tol, (name, frac_bad, rel_l2, l2_tol, float(diff.max()), tol)
+    l2_tol = max(1e-4, 10 * floor * ref.numel() ** 0.5 / max(1e-12, float(ref.double().norm())))
+    assert worst <= tol and rel_l2 <= l2_tol, (name, worst, tol, rel_l2, l2_tol)
 
 
 @pytest.mark.parametrize("n_scenes,n_obj,n_pts,pairs,image", [(2, 3, 1500, "ordered", False), (3, 4, 1024, "unordered", True),
@@ -158,12 +190,21 @@ def test_multi_scene_batch_against_oracle(cuda, n_scenes, n_obj, n_pts, pairs, i
     sd = weights.synth_state_dict(seed=1, image=image)
     batch = synthetic.make_batch(10, n_scenes, n_obj=n_obj, n_points_obj=n_pts, n_points_rel=n_pts + 200, pairs=pairs,
                                  image=image)
-    ref = _oracle_run(sd, batch, 0.1, image)
-    s, want, want_loss = ref
-    out_floor, grad_floor = _noise_floor(sd, batch, 0.1, ref, image)
+    from sg4d import mlp
     m = _model(cuda, sd, 0.1, image)
     db = synthetic.to_device(batch, cuda)
-    outs = m(db, return_meta_data=True)
+    mlp.CAPTURE = []
+    try:
+        outs = m(db, return_meta_data=True)
+        pins = _pins_from_captures(mlp.CAPTURE)
+    finally:
+        mlp.CAPTURE = None
+    ref = _oracle_run(sd, batch, 0.1, image, pins=pins)
+    s, want, want_loss = ref
+    out_floor, grad_floor = _noise_floor(sd, batch, 0.1, ref, image, pins=pins)
+    free = _oracle_run(sd, batch, 0.1, image)          # the oracle with its OWN selections: forward values must agree too
+    for name, a, b in zip(OUT_NAMES[2:4], want[2:4], free[1][2:4]):
+        assert float((a - b).abs().max()) <= 1e-5, name    # pinning only resolves near-ties
     for name, a, b in zip(OUT_NAMES, outs, want):
         tol = 1e-4 if name.endswith("_feature") and not name.startswith("gcn") else max(1e-4, 10 * out_floor[name])
         torch.testing.assert_close(a.detach().cpu(), b.detach(), rtol=0, atol=tol, msg=lambda s_: name + ": " + s_)

@@ -1,8 +1,8 @@
 """Turns an ncu CSV (--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum) of a short bench run
-into profiles/r01_ncu_traffic.json: per kernel, launches / time / DRAM bytes of ONE step (the launches between the
+into profiles/r02_ncu_traffic.json: per kernel, launches / time / DRAM bytes of ONE step (the launches between the
 last two pairs of cloud_box_kernel markers).
 
-    python tools/ncu_traffic.py gpurun_out/r01_traffic.csv profiles/r01_ncu_traffic.json
+    python tools/ncu_traffic.py gpurun_out/r02_traffic.csv profiles/r02_ncu_traffic.json
 """
 import collections
 import csv
