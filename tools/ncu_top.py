@@ -5,6 +5,7 @@ import sys
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+sel = sys.argv[3] if len(sys.argv) > 3 else None
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 blocks, cur = [], None
@@ -16,7 +17,11 @@ for r in rows:
         cur["hdr"] = r
     elif cur is not None and cur["hdr"] is not None and len(r) == len(cur["hdr"]):
         cur["rows"].append(r)
-for blk in blocks[:1]:
+seen = set()
+for blk in ([b for b in blocks if sel in b["name"]] if sel else blocks[:1]):
+    if blk["name"] in seen:
+        continue
+    seen.add(blk["name"])
     h = blk["hdr"]
     si = h.index("# Samples")
     stall = [i for i, c in enumerate(h) if c.startswith("stall_") and "Not Issued" not in c]
