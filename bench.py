@@ -509,7 +509,7 @@ def main_sg4d(args):
             rows, n_, m_, ns_, ps_, fs_ = a[:6]       # then [foff,] c, n2 (zero-valued arguments are not recorded)
             n2 = a[-1] if nm != "sg4d_sa_moments" else 0
             clouds = rows // (m_ * ns_)
-            cloud_bytes = clouds * n_ * ps_ * 4       # the gathered cloud, once
+            cloud_bytes = min(clouds * n_, rows) * ps_ * 4      # the gathered points, each at most once
             pooled = (rows // ns_) * n2 * 5
             if nm == "sg4d_sa_moments":
                 return rows * 4 + cloud_bytes, 0
