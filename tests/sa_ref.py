@@ -8,6 +8,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from oracle.pins import grouped_fp64, h1_mask  # noqa: F401  (shared with the model-level checks)
+
 EPS = 1e-5
 
 
@@ -40,33 +42,6 @@ def shared_mlp_rows(mlp: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
             raise TypeError(f"unexpected layer in shared MLP: {type(layer).__name__}")
     return x
 
-
-
-def grouped_fp64(pts, feats, foff, c, centers, idx):
-    """reference grouped rows [xyz - centre | feats] (utils.py:319-328), fp64, differentiable w.r.t. feats"""
-    b, n, _ = pts.shape
-    m, ns = idx.shape[1], idx.shape[2]
-    li = idx.long().view(b, m * ns)
-    xyz = torch.gather(pts[:, :, :3].double(), 1, li.unsqueeze(-1).expand(-1, -1, 3)).view(b, m, ns, 3)
-    xyz = (xyz.float() - centers.view(b, m, 1, 3)).double()           # the reference subtracts in fp32
-    cols = [xyz]
-    if c:
-        f = feats[:, :, foff:foff + c]
-        cols.append(torch.gather(f, 1, li.unsqueeze(-1).expand(-1, -1, c)).view(b, m, ns, c).double())
-    return torch.cat(cols, dim=3).view(b * m * ns, 3 + c)
-
-
-def h1_mask(cap, x32):
-    """The first layer's ReLU mask exactly as the kernels evaluate it (fp32 fused multiply-adds in the kernel's order):
-    the second pinned selection -- an activation within rounding of 0 may be clipped on one side only."""
-    if cap["kind"] == "sa1":
-        w1s, t1 = cap["w1s"], cap["stats1"][1]
-        xa = torch.cat([x32, torch.zeros(x32.shape[0], 8 - x32.shape[1], device=x32.device)], 1)
-        v = t1.expand(x32.shape[0], 64).clone()
-        for j in range(8):
-            v = torch.addcmul(v, xa[:, j:j + 1], w1s[j:j + 1])       # fma(x_j, w_j, v), j ascending (sa1_y1bn)
-        return v > 0
-    return torch.addcmul(cap["t1"], cap["y1"], cap["s1"]) > 0
 
 
 def ref_scale(x, params, ns, garg, out_mask, h1_mask):

@@ -10,6 +10,7 @@ import pytest
 import torch
 
 from oracle import model_ref, weights
+from oracle.pins import pins_from_captures as _pins_from_captures
 
 pytestmark = pytest.mark.gpu
 
@@ -97,38 +98,6 @@ def test_model_against_reference_fixture(cuda, golden_dir):
         eo = m(batch)
     np.testing.assert_allclose(eo[0].cpu().numpy(), fx["eval_obj_cls"], rtol=0, atol=max(1e-4, 10 * out_floor["obj_cls"]))
     np.testing.assert_allclose(eo[1].cpu().numpy(), fx["eval_rel_cls"], rtol=0, atol=max(1e-4, 10 * out_floor["rel_cls"]))
-
-
-def _pins_from_captures(caps):
-    """sg4d's selections (max-pool rows, the two ReLU active sets) of every set-abstraction scale, in the oracle's
-    channel-major layout and keyed by the oracle's module prefixes.  Capture order = call order: the object encoder's five
-    scales (SA1 x 2, SA2 x 2, SA3), then the edge encoder's."""
-    import sa_ref
-    pins, scales, inputs = {}, [], None
-    for q in caps:
-        if "mlp" in q:
-            inputs = q
-        elif "garg" in q:
-            scales.append((inputs if q["kind"] in ("sa1", "sa2") else None, q))
-            inputs = None
-    assert len(scales) == 10, len(scales)
-    names = [(enc, lvl, sc) for enc in ("obj_encoder", "rel_encoder") for lvl, sc in ((0, 0), (0, 1), (1, 0), (1, 1), (2, 0))]
-    for (enc, lvl, sc), (inp, q) in zip(names, scales):
-        g, c2 = q["garg"].shape
-        if inp is not None:
-            b, m, ns = inp["idx"].shape
-            x32 = sa_ref.grouped_fp64(inp["pts"], inp["feats"] if inp["feats"] is not None else inp["pts"], inp["foff"], inp["c"],
-                                      inp["centers"], inp["idx"]).float()
-            h1 = sa_ref.h1_mask(q, x32)
-        else:                                   # SA3 (GroupAll): one group of n points per cloud
-            h1 = sa_ref.h1_mask(q, None)
-            b, m, ns = g, 1, h1.shape[0] // g
-        c2 = q["out"].shape[1]
-        pins[f"{enc}.backbone.SA_modules.{lvl}.{sc}"] = (
-            h1.view(b, m, ns, -1).permute(0, 3, 1, 2).float().cpu(),
-            q["garg"][:, :c2].view(b, m, c2).permute(0, 2, 1).unsqueeze(-1).long().cpu(),
-            (q["out"] > 0).view(b, m, c2).permute(0, 2, 1).float().cpu())
-    return pins
 
 
 def _oracle_run(sd, batch, lambda_o, image=False, w_obj=None, w_rel=None, jitter_seed=None, pins=None):
