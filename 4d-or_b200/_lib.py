@@ -33,6 +33,9 @@ SIGNATURES = {
     "sg4d_ball_query_rows": [_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "sg4d_group_rows": [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
     "sg4d_group_rows_grad": [_i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "sg4d_group_rows_grad_dy": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "sg4d_gather_y1": [_i64, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
+    "sg4d_group_sum_dy": [_i64, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "sg4d_spatial_index_build": [_i, _i, _i, _p, _p, _p],
     "sg4d_fps_indexed": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
     "sg4d_ball_query_rows_indexed": [_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p],
@@ -73,7 +76,7 @@ OTHER_SYMBOLS = ["sg4d_abi_version", "sg4d_error_string", "sg4d_check_device", "
                  "sg4d_spatial_index_supported", "sg4d_sa_moments_parts", "sg4d_sa1_s1part_doubles",
                  "sg4d_dense_weight_floats", "sg4d_dense_partial_doubles", "sg4d_colsum_part_doubles",
                  "sg4d_dense_wgrad_partial_floats", "sg4d_frontend_workspace_bytes", "sg4d_set_compute_precision",
-                 "sg4d_get_compute_precision"]
+                 "sg4d_get_compute_precision", "sg4d_gather_y1_parts"]
 
 _lib = None
 
@@ -109,6 +112,7 @@ def load():
         lib.sg4d_frontend_workspace_bytes.argtypes, lib.sg4d_frontend_workspace_bytes.restype = [_i, _i, _i], _i64
         lib.sg4d_set_compute_precision.argtypes, lib.sg4d_set_compute_precision.restype = [_i], _i
         lib.sg4d_get_compute_precision.argtypes, lib.sg4d_get_compute_precision.restype = [], _i
+        lib.sg4d_gather_y1_parts.argtypes, lib.sg4d_gather_y1_parts.restype = [_i], _i
         if lib.sg4d_abi_version() != 1:
             raise RuntimeError("libsg4d.so ABI version mismatch; rebuild it")
         _lib = lib

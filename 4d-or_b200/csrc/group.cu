@@ -180,11 +180,17 @@ group_rows_wide4_kernel(long long rows, int n, int m, int nsample, int c, int pt
 // accumulates c/32 channels with coalesced 128-byte reads of grad_out.
 constexpr int kGgWarps = 16;
 // V4: the feature columns are 16-byte aligned (gcol0, out_stride, c multiples of 4): lanes accumulate float4 columns
-template <bool V4>
+// DY: the summed rows are not stored anywhere -- they are the first layer's dY1 = p .* dz1 - (q .* y1 + u), evaluated from dz1
+//     (= grad_out) and y1 while they are summed (c = C1 <= 128 channels, V4 layout).  Because dX = dY1 W1 is linear, the
+//     feature gradient of a source point is (sum of its rows' dY1) W1: one small GEMM over B*n rows afterwards replaces the
+//     dX GEMM over all B*m*nsample grouped rows and the (rows x 196) dX tensor it wrote for this kernel to read back.
+template <bool V4, bool DY = false>
 __global__ void __launch_bounds__(kGgWarps * 32)
 group_rows_grad_kernel(int n, int m, int nsample, int c, int out_stride, int gcol0, int slices, int accumulate,
                        const float *__restrict__ grad_out, const int32_t *__restrict__ idx,
-                       const int32_t *__restrict__ cnt, float *__restrict__ grad_feats) {
+                       const int32_t *__restrict__ cnt, float *__restrict__ grad_feats, const float *__restrict__ y1 = nullptr,
+                       const float *__restrict__ p1 = nullptr, const float *__restrict__ q1 = nullptr,
+                       const float *__restrict__ u1 = nullptr) {
     extern __shared__ int32_t s_idx[];  // (m, nsample) indices of this cloud, then (m) counts
     int32_t *s_cnt = s_idx + (size_t)m * nsample;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -193,6 +199,14 @@ group_rows_grad_kernel(int n, int m, int nsample, int c, int out_stride, int gco
     cnt += (size_t)cloud * m;
     grad_out += (size_t)cloud * m * nsample * out_stride;
     grad_feats += (size_t)cloud * n * c;
+    float4 pv = make_float4(0.f, 0.f, 0.f, 0.f), qv = pv, uv = pv;
+    if (DY) {
+        y1 += (size_t)cloud * m * nsample * out_stride;
+        if (lane < (c >> 2)) {
+            pv = __ldg(reinterpret_cast<const float4 *>(p1) + lane), qv = __ldg(reinterpret_cast<const float4 *>(q1) + lane);
+            uv = __ldg(reinterpret_cast<const float4 *>(u1) + lane);
+        }
+    }
     for (int e = tid; e < m * nsample; e += kGgWarps * 32) s_idx[e] = __ldg(idx + e);
     for (int e = tid; e < m; e += kGgWarps * 32) s_cnt[e] = __ldg(cnt + e);
     __syncthreads();
@@ -235,7 +249,14 @@ group_rows_grad_kernel(int n, int m, int nsample, int c, int out_stride, int gco
                 int k = pp;
                 while (k < nsample) {
                     const float *gr = g + (size_t)k * out_stride;
-                    if (V4) {
+                    if (DY) {      // c <= 128: one float4 column group per lane
+                        if (lane < c4) {
+                            const float4 dz = __ldg(reinterpret_cast<const float4 *>(gr) + lane);
+                            const float4 yy = __ldg(reinterpret_cast<const float4 *>(y1 + ((size_t)jj * nsample + k) * out_stride) + lane);
+                            acc[0] += fmaf(dz.x, pv.x, -fmaf(yy.x, qv.x, uv.x)), acc[1] += fmaf(dz.y, pv.y, -fmaf(yy.y, qv.y, uv.y));
+                            acc[2] += fmaf(dz.z, pv.z, -fmaf(yy.z, qv.z, uv.z)), acc[3] += fmaf(dz.w, pv.w, -fmaf(yy.w, qv.w, uv.w));
+                        }
+                    } else if (V4) {
 #pragma unroll
                         for (int v = 0; v < kMaxChunk / 4; ++v) {
                             const int q4 = lane + 32 * v;
@@ -373,5 +394,124 @@ extern "C" int sg4d_group_rows_grad(int b, int n, int m, int nsample, int c, int
     else
         group_rows_grad_kernel<false><<<(unsigned)(b * slices), kGgWarps * 32, smem, (cudaStream_t)stream>>>(
             n, m, nsample, c, out_stride, gcol0, slices, accumulate, grad_out, idx, cnt, grad_feats);
+    return SG4D_LAUNCH_CHECK();
+}
+
+// G (b, n, c1) = per source point, the sum of dY1 = p1 .* dz1 - (q1 .* y1 + u1) over the grouped rows that reference it
+// (deterministic gather, fixed order).  dz1 / y1 (b*m*nsample, c1), c1 in {64, 128}.  The feature gradient is G * W1[:, feats].
+extern "C" int sg4d_group_rows_grad_dy(int b, int n, int m, int nsample, int c1, const float *y1, const float *dz1,
+                                       const float *p1, const float *q1, const float *u1, const int32_t *idx,
+                                       const int32_t *cnt, float *g_out, sg4d_stream_t stream) {
+    if (b < 0 || n <= 0 || m <= 0 || nsample <= 0 || (c1 != 64 && c1 != 128) || !y1 || !dz1 || !p1 || !q1 || !u1 || !idx || !cnt ||
+        !g_out || ((reinterpret_cast<uintptr_t>(y1) | reinterpret_cast<uintptr_t>(dz1) | reinterpret_cast<uintptr_t>(g_out)) & 15))
+        return SG4D_EINVAL;
+    if (b == 0) return SG4D_OK;
+    const size_t smem = ((size_t)m * nsample + m) * sizeof(int32_t);
+    if (smem > 200 * 1024) return SG4D_EINVAL;
+    cudaError_t e = cudaFuncSetAttribute(group_rows_grad_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return status_of(e);
+    int slices = 1;
+    while ((long long)b * slices < 4LL * SG4D_NUM_SMS && slices * kGgWarps * 2 <= n) slices *= 2;
+    group_rows_grad_kernel<true, true><<<(unsigned)(b * slices), kGgWarps * 32, smem, (cudaStream_t)stream>>>(
+        n, m, nsample, c1, c1, 0, slices, 0, dz1, idx, cnt, g_out, y1, p1, q1, u1);
+    return SG4D_LAUNCH_CHECK();
+}
+
+// ================================================================================================
+// SA2 through its linearity.  The first layer of a scale is linear in the grouped row x = [feats(i) | xyz(i) - centre_j], so
+//     y1[r] = W1 x[r] = Z[i] - Cc[j],      Z = [feats | xyz] W1^T  per SOURCE POINT (b*n rows),  Cc = centre W1x^T per centre:
+// one small GEMM over the b*n source points replaces the GEMM over all b*m*nsample grouped rows (24x fewer rows at SA2), and the
+// forward pass of the layer becomes the gather below.  The backward pass uses the same linearity: with G[i] = sum of dY1 over the
+// rows that reference point i (sg4d_group_rows_grad_dy) and H[j] = sum of dY1 over the rows of centre j (group_sum_dy_kernel),
+//     dFeats = G W1f,    dW1 = G^T [feats | xyz] - H^T [0 | centre].
+namespace sg4d {
+
+// y1[r, :] = Z[cloud * n + idx[r], :] - Cc[r / nsample, :]; per-channel sum / sum of squares as fp64 partial pairs in the layout
+// sg4d_bn_finalize reads (pair index % C1 = channel).  blockDim = 256 = (C1 / 4 column groups) x (row lanes); fixed grid.
+__global__ void __launch_bounds__(256)
+gather_y1_kernel(long long rows, int n, int m, int nsample, int c1, const float *__restrict__ Z, const float *__restrict__ Cc,
+                 const int32_t *__restrict__ idx, float *__restrict__ y1, double *__restrict__ partial) {
+    const int vec = c1 >> 2, lanes = 256 / vec;
+    const int cg = threadIdx.x % vec, rl = threadIdx.x / vec;
+    const long long per_cloud = (long long)m * nsample;
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+    double ds[4] = {0.0, 0.0, 0.0, 0.0}, dq[4] = {0.0, 0.0, 0.0, 0.0};
+    int since = 0;
+    for (long long r = (long long)blockIdx.x * lanes + rl; r < rows; r += (long long)gridDim.x * lanes) {
+        const long long cloud = r / per_cloud;
+        const long long g = r / nsample;
+        const float4 z = __ldg(reinterpret_cast<const float4 *>(Z + (cloud * n + __ldg(idx + r)) * c1) + cg);
+        const float4 c = __ldg(reinterpret_cast<const float4 *>(Cc + g * c1) + cg);
+        const float4 y = make_float4(z.x - c.x, z.y - c.y, z.z - c.z, z.w - c.w);
+        reinterpret_cast<float4 *>(y1 + r * c1)[cg] = y;
+        s[0] += y.x, s[1] += y.y, s[2] += y.z, s[3] += y.w;
+        q[0] = fmaf(y.x, y.x, q[0]), q[1] = fmaf(y.y, y.y, q[1]), q[2] = fmaf(y.z, y.z, q[2]), q[3] = fmaf(y.w, y.w, q[3]);
+        if (++since == 64) {   // fp32 over short runs, fp64 across them
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ds[u] += (double)s[u], dq[u] += (double)q[u], s[u] = 0.f, q[u] = 0.f;
+            since = 0;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const size_t i = ((size_t)blockIdx.x * lanes + rl) * c1 + 4 * cg + u;
+        partial[2 * i] = ds[u] + (double)s[u];
+        partial[2 * i + 1] = dq[u] + (double)q[u];
+    }
+}
+
+// H[j, :] = sum over the nsample rows of centre j of dY1 = p .* dz1 - (q .* y1 + u).  One warp per (group, 128-column chunk).
+__global__ void __launch_bounds__(256)
+group_sum_dy_kernel(long long groups, int nsample, int c1, const float *__restrict__ y1, const float *__restrict__ dz1,
+                    const float *__restrict__ p1, const float *__restrict__ q1, const float *__restrict__ u1, float *__restrict__ H) {
+    const int lane = threadIdx.x & 31, vec = c1 >> 2;
+    if (lane >= vec) return;
+    const float4 pv = __ldg(reinterpret_cast<const float4 *>(p1) + lane), qv = __ldg(reinterpret_cast<const float4 *>(q1) + lane);
+    const float4 uv = __ldg(reinterpret_cast<const float4 *>(u1) + lane);
+    const long long nwarp = ((long long)gridDim.x * 256) >> 5;
+    for (long long g = (blockIdx.x * 256LL + threadIdx.x) >> 5; g < groups; g += nwarp) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float *dz = dz1 + g * nsample * c1, *yy = y1 + g * nsample * c1;
+        for (int k = 0; k < nsample; k += 2) {     // two rows in flight
+            const float4 d0 = __ldg(reinterpret_cast<const float4 *>(dz + (size_t)k * c1) + lane);
+            const float4 y0 = __ldg(reinterpret_cast<const float4 *>(yy + (size_t)k * c1) + lane);
+            float4 d1 = make_float4(0.f, 0.f, 0.f, 0.f), y1v = d1;
+            const bool two = k + 1 < nsample;
+            if (two) {
+                d1 = __ldg(reinterpret_cast<const float4 *>(dz + (size_t)(k + 1) * c1) + lane);
+                y1v = __ldg(reinterpret_cast<const float4 *>(yy + (size_t)(k + 1) * c1) + lane);
+            }
+            acc.x += fmaf(d0.x, pv.x, -fmaf(y0.x, qv.x, uv.x)), acc.y += fmaf(d0.y, pv.y, -fmaf(y0.y, qv.y, uv.y));
+            acc.z += fmaf(d0.z, pv.z, -fmaf(y0.z, qv.z, uv.z)), acc.w += fmaf(d0.w, pv.w, -fmaf(y0.w, qv.w, uv.w));
+            if (two) {
+                acc.x += fmaf(d1.x, pv.x, -fmaf(y1v.x, qv.x, uv.x)), acc.y += fmaf(d1.y, pv.y, -fmaf(y1v.y, qv.y, uv.y));
+                acc.z += fmaf(d1.z, pv.z, -fmaf(y1v.z, qv.z, uv.z)), acc.w += fmaf(d1.w, pv.w, -fmaf(y1v.w, qv.w, uv.w));
+            }
+        }
+        reinterpret_cast<float4 *>(H + g * c1)[lane] = acc;
+    }
+}
+
+}  // namespace sg4d
+
+extern "C" int sg4d_gather_y1_parts(int c1) { return SG4D_NUM_SMS * 8 * (256 / (c1 >> 2)) * c1; }   // fp64 PAIRS
+
+extern "C" int sg4d_gather_y1(long long rows, int n, int m, int nsample, int c1, const float *z, const float *cc,
+                              const int32_t *idx, float *y1, double *partial, sg4d_stream_t stream) {
+    if (rows <= 0 || n <= 0 || m <= 0 || nsample <= 0 || (c1 != 64 && c1 != 128) || rows % ((long long)m * nsample) || !z || !cc ||
+        !idx || !y1 || !partial || ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(cc) | reinterpret_cast<uintptr_t>(y1)) & 15))
+        return SG4D_EINVAL;
+    gather_y1_kernel<<<SG4D_NUM_SMS * 8, 256, 0, (cudaStream_t)stream>>>(rows, n, m, nsample, c1, z, cc, idx, y1, partial);
+    return SG4D_LAUNCH_CHECK();
+}
+
+extern "C" int sg4d_group_sum_dy(long long groups, int nsample, int c1, const float *y1, const float *dz1, const float *p1,
+                                 const float *q1, const float *u1, float *h, sg4d_stream_t stream) {
+    if (groups <= 0 || nsample <= 0 || (c1 != 64 && c1 != 128) || !y1 || !dz1 || !p1 || !q1 || !u1 || !h ||
+        ((reinterpret_cast<uintptr_t>(y1) | reinterpret_cast<uintptr_t>(dz1) | reinterpret_cast<uintptr_t>(h)) & 15))
+        return SG4D_EINVAL;
+    long long blocks = (groups + 7) / 8;
+    if (blocks > SG4D_NUM_SMS * 32) blocks = SG4D_NUM_SMS * 32;
+    group_sum_dy_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(groups, nsample, c1, y1, dz1, p1, q1, u1, h);
     return SG4D_LAUNCH_CHECK();
 }

@@ -775,11 +775,23 @@ __global__ void __launch_bounds__(PT + 32 + kEpiThreads, 1) row_gemm_kernel(RowG
             } else if (p.Y) {   // coalesced store of the tile: 16 bytes per thread per step
                 float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (EMODE == 2 && q_bias) bv = __ldg(reinterpret_cast<const float4 *>(q_bias + (e % kVecPerRow) * 4));   // kEpiThreads % kVecPerRow == 0: my columns are fixed
-                for (int v4 = e; v4 < nvalid * kVecPerRow; v4 += kEpiThreads) {
-                    const int r = v4 / kVecPerRow, cc = (v4 % kVecPerRow) * 4;
-                    float4 v = *reinterpret_cast<const float4 *>(Cs + r * SM::kCStride + cc);
-                    if (EMODE == 2) v.x += bv.x, v.y += bv.y, v.z += bv.z, v.w += bv.w;
-                    *reinterpret_cast<float4 *>(p.Y + (row0 + r) * p.ldy + q_ycol0 + cc) = v;
+                // my column group is fixed (kEpiThreads % kVecPerRow == 0); rows rb, rb + kRowStep, ...  Eight shared-memory
+                // loads are issued before the first store (the one-at-a-time loop spent 2.7 k cycles per tile on LDS latency)
+                const int cc = (e % kVecPerRow) * 4, rb = e / kVecPerRow;
+                const float *cs = Cs + rb * SM::kCStride + cc;
+                float *yp = p.Y + (row0 + rb) * p.ldy + q_ycol0 + cc;
+                const long long ystep = (long long)kRowStep * p.ldy;
+                constexpr int kPerThread = kTileM / kRowStep;
+#pragma unroll
+                for (int b8 = 0; b8 < kPerThread; b8 += 8) {
+                    float4 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4 *>(cs + (b8 + u) * kRowStep * SM::kCStride);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (EMODE == 2) v[u].x += bv.x, v[u].y += bv.y, v[u].z += bv.z, v[u].w += bv.w;
+                        if (rb + (b8 + u) * kRowStep < nvalid) *reinterpret_cast<float4 *>(yp + (b8 + u) * ystep) = v[u];
+                    }
                 }
             }
             SG4D_TRACE(e == 0 && ti < 256, 5120 + (int)ti * 5 + 3);

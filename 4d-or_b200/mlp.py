@@ -292,51 +292,62 @@ class _FusedSA1(torch.autograd.Function):
 
 
 class _FusedSA2(torch.autograd.Function):
-    """One scale of a set-abstraction level whose input features carry a gradient (c % 4 == 0 channels): the grouped
-    rows [feats(idx) | xyz(idx) - centre | 0] are gathered by the operand stagers of the first layer and of its
-    weight-gradient kernel instead of being written to and read back from HBM.  w1 (n1, 3 + c), reference column order."""
+    """One scale of a set-abstraction level whose input features carry a gradient.  The first layer is linear in the grouped
+    row x = [feats(i) | xyz(i) - centre_j], so it is evaluated per SOURCE POINT (one small GEMM over the b*n points) and the
+    grouped first-layer activations are a gather:  y1[r] = Z[i(r)] - Cc[j(r)].  The backward pass uses the same linearity:
+    G[i] = sum of dY1 over the rows that reference point i, H[j] = sum of dY1 over the rows of centre j,
+    dFeats = G W1f,  dW1 = G^T [feats | xyz] - H^T [0 | centre].  Neither the grouped tensor nor a GEMM with K = 3 + c over the
+    b*m*nsample grouped rows exists in either direction.  w1 (n1, 3 + c), reference column order [xyz | feats]."""
 
     @staticmethod
     def forward(ctx, pts, feats, centers, idx, cnt, w1, g1, be1, w2, g2, be2, foff, c, bn1, bn2):
-        src = _src_args(pts, feats, foff, c, centers, idx)
-        rows, dev = src[0], pts.device
-        n1, n2, ns = w1.shape[0], w2.shape[0], idx.shape[2]
+        from . import dense
+        dev = pts.device
+        b, n = pts.shape[0], pts.shape[1]
+        m, ns = idx.shape[1], idx.shape[2]
+        rows = b * m * ns
+        n1, n2 = w1.shape[0], w2.shape[0]
         lib = _lib.load()
-        w1g = F.pad(torch.cat([w1[:, 3:], w1[:, :3]], dim=1), (0, 1))        # grouped column order [feats | xyz | 0]
+        w1g = F.pad(torch.cat([w1[:, 3:], w1[:, :3]], dim=1), (0, 1))        # column order [feats | xyz | 0]
+        xin = torch.cat([feats[..., foff:foff + c].reshape(b * n, c), pts[..., :3].reshape(b * n, 3),
+                         torch.zeros(b * n, 1, dtype=torch.float32, device=dev)], dim=1)
+        cen4 = F.pad(centers.reshape(b * m, 3), (0, 1))
+        z = dense._fwd(xin, c + 4, dense.pack(w1g), n1)[0]                    # per source point
+        cc = dense._fwd(cen4, 4, dense.pack(w1g[:, c:].contiguous()), n1)[0]  # per centre
         y1 = torch.empty(rows, n1, dtype=torch.float32, device=dev)
-        part1 = torch.empty(lib.sg4d_mlp_partial_doubles(rows), dtype=torch.float64, device=dev)
-        _lib.call("sg4d_linear_fwd_grouped", pts, *src, n1, pack_weight(w1g).data_ptr(), y1.data_ptr(), part1.data_ptr())
+        part1 = torch.empty(2 * lib.sg4d_gather_y1_parts(n1), dtype=torch.float64, device=dev)
+        _lib.call("sg4d_gather_y1", pts, rows, n, m, ns, n1, z.data_ptr(), cc.data_ptr(), idx.data_ptr(), y1.data_ptr(),
+                  part1.data_ptr())
         s1, t1, m1, i1 = bn_scale_shift(bn1, part1, rows)
         y2, part2, gsel, garg = linear_fwd(y1, n1, pack_weight(w2), n2, scale=s1, shift=t1, group=ns, gamma=g2)
         s2, t2, m2, i2 = bn_scale_shift(bn2, part2, rows)
         out = torch.relu(torch.addcmul(t2, gsel, s2))
         _capture(kind="sa2", garg=garg, gsel=gsel, y1=y1, y2=y2, s1=s1, t1=t1, out=out)
-        ctx.save_for_backward(pts, feats, centers, idx, cnt, y1, y2, gsel, garg, out, w1g, w2, s1, t1, m1, i1, s2, m2, i2)
-        ctx.meta = (foff, c, bn1.training or not bn1.track_running_stats, bn2.training or not bn2.track_running_stats)
+        ctx.save_for_backward(xin, cen4, idx, cnt, y1, y2, gsel, garg, out, w1g, w2, s1, t1, m1, i1, s2, m2, i2)
+        ctx.meta = (b, n, c, bn1.training or not bn1.track_running_stats, bn2.training or not bn2.track_running_stats)
+        ctx.foff, ctx.feat_width = foff, feats.shape[2]
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        pts, feats, centers, idx, cnt, y1, y2, gsel, garg, out, w1g, w2, s1, t1, m1, i1, s2, m2, i2 = ctx.saved_tensors
-        foff, c, batch1, batch2 = ctx.meta
-        src = _src_args(pts, feats, foff, c, centers, idx)
-        rows, dev = src[0], pts.device
-        n1, n2, ns = w1g.shape[0], w2.shape[0], idx.shape[2]
-        b, n = pts.shape[0], pts.shape[1]
-        m = idx.shape[1]
-        kp = c + 4
-        dsel, a2, b2, d_g2, d_be2 = _pool_bwd_consts(d_out, out, gsel, s2, m2, i2, rows, batch2, pts)
+        from . import dense
+        xin, cen4, idx, cnt, y1, y2, gsel, garg, out, w1g, w2, s1, t1, m1, i1, s2, m2, i2 = ctx.saved_tensors
+        b, n, c, batch1, batch2 = ctx.meta
+        m, ns = idx.shape[1], idx.shape[2]
+        rows, dev = b * m * ns, xin.device
+        n1, n2 = w1g.shape[0], w2.shape[0]
+        dsel, a2, b2, d_g2, d_be2 = _pool_bwd_consts(d_out, out, gsel, s2, m2, i2, rows, batch2, xin)
         em1 = (-m1 * i1).contiguous()
         dz1 = torch.empty(rows, n1, dtype=torch.float32, device=dev)
         part = torch.empty(_lib.load().sg4d_mlp_partial_doubles(rows), dtype=torch.float64, device=dev)
-        _lib.call("sg4d_pool_bwd_da", pts, rows, n2, n1, ns, y2.data_ptr(), a2.data_ptr(), b2.data_ptr(), dsel.data_ptr(),
+        _lib.call("sg4d_pool_bwd_da", xin, rows, n2, n1, ns, y2.data_ptr(), a2.data_ptr(), b2.data_ptr(), dsel.data_ptr(),
                   garg.data_ptr(), pack_weight(w2.t()).data_ptr(), y1.data_ptr(), s1.data_ptr(), t1.data_ptr(),
                   i1.data_ptr(), em1.data_ptr(), dz1.data_ptr(), part.data_ptr())
         sums = torch.empty(2, n1, dtype=torch.float32, device=dev)
-        _lib.call("sg4d_partial_sums", pts, n1, part.numel() // 2, part.data_ptr(), sums.data_ptr())
+        _lib.call("sg4d_partial_sums", xin, n1, part.numel() // 2, part.data_ptr(), sums.data_ptr())
         d_be1, d_g1 = sums[0], sums[1]
         d_w2 = torch.empty(n2, n1, dtype=torch.float32, device=dev)
-        _lib.call("sg4d_pool_bwd_dw", pts, rows, n2, n1, ns, y2.data_ptr(), a2.data_ptr(), b2.data_ptr(), dsel.data_ptr(),
+        _lib.call("sg4d_pool_bwd_dw", xin, rows, n2, n1, ns, y2.data_ptr(), a2.data_ptr(), b2.data_ptr(), dsel.data_ptr(),
                   garg.data_ptr(), y1.data_ptr(), s1.data_ptr(), t1.data_ptr(), _wgrad_partial(rows, n1, dev).data_ptr(),
                   d_w2.data_ptr())
         p1 = s1.contiguous()
@@ -346,24 +357,26 @@ class _FusedSA2(torch.autograd.Function):
         else:
             q1 = torch.zeros_like(s1)
             u1 = torch.zeros_like(s1)
-        d_w1g = torch.empty(n1, c + 3, dtype=torch.float32, device=dev)
-        _lib.call("sg4d_inner_bwd_dw_grouped", pts, *src, n1, y1.data_ptr(), dz1.data_ptr(), p1.data_ptr(), q1.data_ptr(),
-                  u1.data_ptr(), _wgrad_partial(rows, 224, dev).data_ptr(), d_w1g.data_ptr(), c + 3)
-        d_w1 = torch.cat([d_w1g[:, c:], d_w1g[:, :c]], dim=1)               # back to the reference order [xyz | feats]
+        # dY1 = p1 .* dz1 - (q1 .* y1 + u1) is never stored: both sums below generate it on the fly
+        g_sum = torch.empty(b * n, n1, dtype=torch.float32, device=dev)      # per source point (deterministic gather)
+        _lib.call("sg4d_group_rows_grad_dy", xin, b, n, m, ns, n1, y1.data_ptr(), dz1.data_ptr(), p1.data_ptr(), q1.data_ptr(),
+                  u1.data_ptr(), idx.data_ptr(), cnt.data_ptr(), g_sum.data_ptr())
+        h_sum = torch.empty(b * m, n1, dtype=torch.float32, device=dev)      # per centre
+        _lib.call("sg4d_group_sum_dy", xin, b * m, ns, n1, y1.data_ptr(), dz1.data_ptr(), p1.data_ptr(), q1.data_ptr(),
+                  u1.data_ptr(), h_sum.data_ptr())
+        d_w1g = dense._dw(b * n, n1, g_sum, 0, xin, c + 4)                    # (n1, c + 4): G^T [feats | xyz | 0]
+        d_wc = dense._dw(b * m, n1, h_sum, 0, cen4, 4)                        # (n1, 4):     H^T [centre | 0]
+        d_w1 = torch.cat([d_w1g[:, c:c + 3] - d_wc[:, :3], d_w1g[:, :c]], dim=1)   # reference order [xyz | feats]
         d_feats = None
         if ctx.needs_input_grad[1]:
-            # dX for the gathered feature columns, then the deterministic scatter back to the source points
-            d_x = torch.empty(rows, kp, dtype=torch.float32, device=dev)
-            col = 0
-            while col < c:
-                nn_ = 128 if c - col >= 128 else 64
-                wt = pack_weight(w1g[:, col:col + nn_].t())
-                _lib.call("sg4d_inner_bwd_dx", pts, rows, n1, nn_, y1.data_ptr(), dz1.data_ptr(), p1.data_ptr(), q1.data_ptr(),
-                          u1.data_ptr(), wt.data_ptr(), d_x.data_ptr(), kp, col)
-                col += nn_
-            d_feats = torch.empty(b, n, c, dtype=torch.float32, device=dev)
-            _lib.call("sg4d_group_rows_grad", pts, b, n, m, ns, c, kp, 0, 0, d_x.data_ptr(), idx.data_ptr(), cnt.data_ptr(),
-                      d_feats.data_ptr())
+            ncol = (c + 63) // 64 * 64
+            wt = F.pad(w1g[:, :c].t(), (0, 0, 0, ncol - c))                 # (ncol, n1) = W1[:, feats]^T, zero rows of padding
+            d = dense._dx(b * n, n1, g_sum, 0, ncol, dense.pack(wt))[:, :c].reshape(b, n, c)
+            if ctx.foff == 0 and ctx.feat_width == c:
+                d_feats = d
+            else:                                                           # the scale reads a column window of a wider tensor
+                d_feats = torch.zeros(b, n, ctx.feat_width, dtype=torch.float32, device=dev)
+                d_feats[..., ctx.foff:ctx.foff + c] = d
         return (None, d_feats, None, None, None, d_w1, d_g1, d_be1, d_w2, d_g2, d_be2, None, None, None, None)
 
 
@@ -390,7 +403,7 @@ def sa_scale_kind(mlp, c, ns, feats_need_grad, feat_stride, foff):
         return None
     if not feats_need_grad and c <= 4 and n1 == 64:
         return "sa1"
-    if n1 in (64, 128) and c % 64 == 0 and 128 < c + 3 <= 224 and feat_stride % 4 == 0 and foff % 4 == 0:
+    if n1 in (64, 128) and c > 0 and c % 4 == 0:
         return "sa2"
     return None
 

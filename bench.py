@@ -492,6 +492,14 @@ def main_sg4d(args):
         if nm == "sg4d_group_rows_grad":
             b_, n_, m_, ns_, c_ = a[:5]
             return b_ * (4 * c_ * m_ * ns_ + 4 * m_ * ns_ + 4 * c_ * n_), 0
+        if nm == "sg4d_group_rows_grad_dy":      # (b, n, m, ns, c1): read idx, y1, dz1 once; write the per-point sums
+            b_, n_, m_, ns_, c_ = a[:5]
+            return b_ * (m_ * ns_ * (4 + 8 * c_) + 4 * c_ * n_), 0
+        if nm == "sg4d_gather_y1":               # (rows, n, m, ns, c1): read idx, Z (once per point), Cc; write y1
+            rows, n_, m_, ns_, c_ = a[:5]
+            return rows * (4 + 4 * c_) + (rows // (m_ * ns_)) * n_ * c_ * 4 + (rows // ns_) * c_ * 4, 0
+        if nm == "sg4d_group_sum_dy":            # (groups, ns, c1): read y1, dz1; write the per-centre sums
+            return a[0] * a[2] * 4 * (2 * a[1] + 1), 0
         if nm in ("sg4d_ball_query_rows", "sg4d_ball_query_rows_indexed"):
             b_, n_, m_ = a[:3]
             return b_ * (12 * n_ + 12 * m_), 0
@@ -555,7 +563,9 @@ def main_sg4d(args):
     family.update({"sg4d_fps_indexed": "fps_indexed_kernel", "sg4d_fps_rows": "fps_onchip_kernel",
                    "sg4d_ball_query_rows_indexed": "ball_query_kernel+ball_query_indexed_kernel",
                    "sg4d_ball_query_rows": "ball_query_kernel", "sg4d_group_rows": "group_rows_kernel",
-                   "sg4d_group_rows_grad": "group_rows_grad_kernel", "sg4d_spatial_index_build": "spatial_build_kernel"})
+                   "sg4d_group_rows_grad": "group_rows_grad_kernel", "sg4d_group_rows_grad_dy": "group_rows_grad_kernel",
+                   "sg4d_gather_y1": "gather_y1_kernel", "sg4d_group_sum_dy": "group_sum_dy_kernel",
+                   "sg4d_spatial_index_build": "spatial_build_kernel"})
     fam = {}
     for k in kernels:
         f = fam.setdefault(family.get(k["call"], k["call"]), {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "launches": 0.0, "calls": set()})
@@ -610,20 +620,22 @@ def main_sg4d(args):
                 bq_ms += k["ms_per_step"]
                 bq_bytes += k.get("algorithmic_bytes", 0) * k["launches_per_step"]
                 calls.add(k["call"])
-            if k["call"] in ("sg4d_sa1_fwd", "sg4d_linear_fwd_grouped", "sg4d_group_rows"):
+            if k["call"] in ("sg4d_sa1_fwd", "sg4d_linear_fwd_grouped", "sg4d_group_rows", "sg4d_gather_y1"):
                 a = k["args"]
-                width = 8 if k["call"] == "sg4d_sa1_fwd" else (a[-2] + 3 if k["call"] == "sg4d_linear_fwd_grouped" else a[4] + 3)
+                # width of the grouped row the op produces: SA1 8 (padded xyz + features), materialised rows 3 + C, and for
+                # the scales evaluated through the first layer's linearity the PROJECTED row (c1 channels) that is gathered
+                width = {"sg4d_sa1_fwd": 8, "sg4d_linear_fwd_grouped": a[-2] + 3, "sg4d_gather_y1": a[4]}.get(k["call"], a[4] + 3)
                 rows_ = a[0] if k["call"] != "sg4d_group_rows" else a[0] * a[2] * a[3]
                 bq_bytes += rows_ * (4 + 4 * width) * k["launches_per_step"]
-                if k["call"] == "sg4d_group_rows":
+                if k["call"] in ("sg4d_group_rows", "sg4d_gather_y1"):   # group kernels that exist as launches of their own
                     bq_ms += k["ms_per_step"]
                 calls.add(k["call"])
         if bq_ms > 0:
             roof["ball_query_plus_group"] = {"achieved": bq_bytes / (bq_ms * 1e-3) / 1e9, "unit": "GB/s",
                                              "frac": bq_bytes / (bq_ms * 1e-3) / 1e9 / peak, "ms_per_step": bq_ms,
                                              "share_of_step": bq_ms / table_ms_per_step, "calls": sorted(calls),
-                                             "note": "time = the ball-query launches (+ group_rows where a scale still "
-                                                     "materialises rows); bytes = query + grouped-output contract"}
+                                             "note": "time = the ball-query launches + the group kernels that run as launches "
+                                                     "of their own (gather_y1, group_rows); bytes = query + grouped-output contract"}
 
     # ---- the REFERENCE ITSELF on this GPU: its own Python over its own kernels (oracle/ref_gpu.py), batch_size = 1 like
     #      its main.py, same synthetic scenes; fp32 with TF32 off, and fp16 autocast (its native `precision=16`)

@@ -153,6 +153,24 @@ int sg4d_group_rows(int b, int n, int m, int nsample, int c, int pts_stride, int
  * (b,m) from sg4d_ball_query_rows; the feature gradients are columns gcol0..gcol0+c-1 of grad_out.
  * grad_feats (b,n,c) is fully overwritten when accumulate == 0
  * and added to (the second scale of an MSG level) when accumulate != 0. */
+/* Same gather over rows that are never stored: g_out (b, n, c1) = per source point, the sum of the first layer's
+ * dY1 = p1 .* dz1 - (q1 .* y1 + u1) over the grouped rows that reference it (y1, dz1: (b*m*nsample, c1), c1 in {64, 128}).
+ * dX = dY1 W1 is linear, so the feature gradient of group_points_grad is then ONE small GEMM g_out * W1[:, feats] over b*n
+ * rows (sg4d_dense_bwd_dx) instead of the dX GEMM over all grouped rows + its (rows x K) tensor. */
+int sg4d_group_rows_grad_dy(int b, int n, int m, int nsample, int c1, const float *y1, const float *dz1, const float *p1,
+                            const float *q1, const float *u1, const int32_t *idx, const int32_t *cnt, float *g_out,
+                            sg4d_stream_t stream);
+/* SA2 through the first layer's linearity: y1[r] = W1 [feats(i) | xyz(i) - centre_j] = z[cloud*n + idx[r]] - cc[r / nsample], with
+ * z = [feats | xyz] W1^T per SOURCE POINT (b*n rows, one small GEMM: sg4d_dense_fwd) and cc = centre W1x^T per centre.  Writes
+ * y1 (rows, c1) and the per-channel (sum, sum of squares) fp64 partial pairs (sg4d_gather_y1_parts(c1) of them) for
+ * sg4d_bn_finalize.  Replaces the first layer's GEMM over all b*m*nsample grouped rows. */
+int sg4d_gather_y1_parts(int c1);
+int sg4d_gather_y1(long long rows, int n, int m, int nsample, int c1, const float *z, const float *cc, const int32_t *idx,
+                   float *y1, double *partial, sg4d_stream_t stream);
+/* h (groups, c1) = per centre, the sum of dY1 = p1 .* dz1 - (q1 .* y1 + u1) over its nsample rows.  With g_out of
+ * sg4d_group_rows_grad_dy:  dW1 = g_out^T [feats | xyz] - h^T [0 | centre]  (two small GEMMs, sg4d_dense_bwd_dw). */
+int sg4d_group_sum_dy(long long groups, int nsample, int c1, const float *y1, const float *dz1, const float *p1,
+                      const float *q1, const float *u1, float *h, sg4d_stream_t stream);
 int sg4d_group_rows_grad(int b, int n, int m, int nsample, int c, int out_stride, int gcol0, int accumulate,
                          const float *grad_out, const int32_t *idx, const int32_t *cnt,
                          float *grad_feats, sg4d_stream_t stream);

@@ -78,7 +78,7 @@ def test_fused_sa1_scale_matches_pinned_fp64(cuda, b, n, m, ns, c_pts, n2, seed)
 
 
 @pytest.mark.parametrize("b,n,m,ns,c_feat,n1,n2,seed", [(2, 512, 128, 32, 192, 128, 128, 6), (1, 300, 50, 64, 192, 128, 128, 7),
-                                                        (2, 128, 33, 16, 192, 64, 64, 8)])
+                                                        (2, 128, 33, 16, 192, 64, 64, 8), (2, 400, 70, 32, 36, 64, 128, 9)])
 def test_fused_sa2_scale_matches_pinned_fp64(cuda, b, n, m, ns, c_feat, n1, n2, seed):
     """SA2-style scale (195 inputs): rows gathered by the operand stagers, gradient back into the source features"""
     _run(cuda, "sa2", b, n, m, ns, 0, c_feat, n1, n2, seed)
@@ -87,3 +87,36 @@ def test_fused_sa2_scale_matches_pinned_fp64(cuda, b, n, m, ns, c_feat, n1, n2, 
 def test_fused_sa1_many_tiles_per_cta(cuda):
     """148 CTAs x several tiles each + a ragged last tile: exercises the persistent mbarrier phases of the gather path"""
     _run(cuda, "sa1", 9, 2000, 333, 32, 4, 0, 64, 128, 11)
+
+
+@pytest.mark.parametrize("b,n,m,ns,c1,seed", [(2, 512, 128, 32, 128, 1), (3, 200, 33, 16, 64, 2), (1, 64, 5, 64, 128, 3)])
+def test_linearity_kernels_match_torch(cuda, b, n, m, ns, c1, seed):
+    """sg4d_gather_y1 (+ its BatchNorm partial sums), sg4d_group_rows_grad_dy and sg4d_group_sum_dy against plain torch"""
+    from sg4d import _lib
+    _, _, _, idx, cnt = _scene(b, n, m, ns, 0, 0, seed)
+    g = torch.Generator().manual_seed(seed)
+    rows = b * m * ns
+    z, cc = torch.randn(b * n, c1, generator=g).to(cuda), torch.randn(b * m, c1, generator=g).to(cuda)
+    di, dn = idx.to(cuda), cnt.to(cuda)
+    y1 = torch.empty(rows, c1, device=cuda)
+    part = torch.empty(2 * _lib.load().sg4d_gather_y1_parts(c1), dtype=torch.float64, device=cuda)
+    _lib.call("sg4d_gather_y1", z, rows, n, m, ns, c1, z.data_ptr(), cc.data_ptr(), di.data_ptr(), y1.data_ptr(), part.data_ptr())
+    flat = (di.long() + (torch.arange(b, device=cuda) * n).view(b, 1, 1)).reshape(-1)
+    want = z[flat] - cc.repeat_interleave(ns, dim=0)
+    assert torch.equal(y1, want)
+    sums = part.view(-1, c1, 2).sum(0)
+    torch.testing.assert_close(sums[:, 0], want.double().sum(0), rtol=1e-6, atol=1e-5)
+    torch.testing.assert_close(sums[:, 1], want.double().pow(2).sum(0), rtol=1e-6, atol=1e-5)
+
+    dz1 = torch.randn(rows, c1, generator=g).to(cuda)
+    p1, q1, u1 = [torch.randn(c1, generator=g).to(cuda) for _ in range(3)]
+    dy = (p1 * dz1 - (q1 * y1 + u1)).double()
+    h = torch.empty(b * m, c1, device=cuda)
+    _lib.call("sg4d_group_sum_dy", z, b * m, ns, c1, y1.data_ptr(), dz1.data_ptr(), p1.data_ptr(), q1.data_ptr(), u1.data_ptr(),
+              h.data_ptr())
+    torch.testing.assert_close(h.double(), dy.view(b * m, ns, c1).sum(1), rtol=1e-5, atol=1e-5)
+    gs = torch.empty(b * n, c1, device=cuda)
+    _lib.call("sg4d_group_rows_grad_dy", z, b, n, m, ns, c1, y1.data_ptr(), dz1.data_ptr(), p1.data_ptr(), q1.data_ptr(),
+              u1.data_ptr(), di.data_ptr(), dn.data_ptr(), gs.data_ptr())
+    want_g = torch.zeros(b * n, c1, dtype=torch.float64, device=cuda).index_add_(0, flat, dy)
+    torch.testing.assert_close(gs.double(), want_g, rtol=1e-5, atol=2e-5)
