@@ -55,6 +55,7 @@ SIGNATURES = {
     "sg4d_sa1_fwd": [_i64] + [_i] * 7 + [_p] * 6 + [_i] + [_p] * 6 + [_p],
     "sg4d_sa1_bwd_da": [_i64] + [_i] * 7 + [_p] * 6 + [_i] + [_p] * 7 + [_p],
     "sg4d_sa1_bwd_dw2": [_i64] + [_i] * 7 + [_p] * 6 + [_i] + [_p] * 7 + [_p],
+    "sg4d_sa1_bwd_dw2_gram": [_i64] + [_i] * 7 + [_p] * 6 + [_i] + [_p] * 7 + [_p],
     "sg4d_sa1_bwd_finalize": [_i, _i64, _p, _p, _p, _i, _p, _i, _p, _i, _p, _p, _p],
     "sg4d_linear_fwd_grouped": [_i64] + [_i] * 7 + [_p] * 4 + [_i] + [_p] * 3 + [_p],
     "sg4d_dense_pack_weight": [_i, _i, _i, _p, _p, _p],
@@ -76,7 +77,8 @@ OTHER_SYMBOLS = ["sg4d_abi_version", "sg4d_error_string", "sg4d_check_device", "
                  "sg4d_spatial_index_supported", "sg4d_sa_moments_parts", "sg4d_sa1_s1part_doubles",
                  "sg4d_dense_weight_floats", "sg4d_dense_partial_doubles", "sg4d_colsum_part_doubles",
                  "sg4d_dense_wgrad_partial_floats", "sg4d_frontend_workspace_bytes", "sg4d_set_compute_precision",
-                 "sg4d_get_compute_precision", "sg4d_gather_y1_parts"]
+                 "sg4d_get_compute_precision", "sg4d_gather_y1_parts",
+                 "sg4d_sa1_bwd_dw2_gram_ws_floats"]
 
 _lib = None
 
@@ -113,6 +115,7 @@ def load():
         lib.sg4d_set_compute_precision.argtypes, lib.sg4d_set_compute_precision.restype = [_i], _i
         lib.sg4d_get_compute_precision.argtypes, lib.sg4d_get_compute_precision.restype = [], _i
         lib.sg4d_gather_y1_parts.argtypes, lib.sg4d_gather_y1_parts.restype = [_i], _i
+        lib.sg4d_sa1_bwd_dw2_gram_ws_floats.argtypes, lib.sg4d_sa1_bwd_dw2_gram_ws_floats.restype = [_i64, _i], _i64
         if lib.sg4d_abi_version() != 1:
             raise RuntimeError("libsg4d.so ABI version mismatch; rebuild it")
         _lib = lib

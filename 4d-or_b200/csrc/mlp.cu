@@ -959,7 +959,9 @@ struct WgSmem {
 };
 
 // MV = valid channels of P (64 or 128): with 64 the upper half of the P tiles is zeroed once and never rewritten, so
-// the producers only transform the 16 valid float4 columns of each row
+// the producers only transform the 16 valid float4 columns of each row.
+// PMODE 6 ("Gram", N = MV = 64): P IS Q -- the producers write the Q operand into the P tiles and the tensor core reads the
+// same tiles as both operands, so D[0..63] = Q^T Q; channel 64 of P is a constant 1, so D[64] = the column sums of Q.
 template <int N, int PMODE, int QMODE, int MV, bool LP = false>
 __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
     // (registers are allocated per 4 warps: 21 warps count as 24, which caps this kernel at 80 registers per thread -- the
@@ -1012,8 +1014,8 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
     }
     if (warp == kProdWarps) tc::tmem_alloc(smem_u32(&s_tmem), 2 * kTmemCols);
     for (int k = tid; k < 256; k += kMlpThreads) {
-        ps[k] = (PMODE != 0 && k < OP.ncols) ? OP.s[k] : 0.f;
-        pt[k] = (PMODE != 0 && k < OP.ncols) ? OP.t[k] : 0.f;
+        ps[k] = (PMODE != 0 && PMODE != 6 && k < OP.ncols) ? OP.s[k] : 0.f;
+        pt[k] = (PMODE != 0 && PMODE != 6 && k < OP.ncols) ? OP.t[k] : 0.f;
         pp[k] = (PMODE == 3 && k < OP.ncols) ? OP.p[k] : 0.f;
         if (QMODE == 4) {      // qs[0..511] (= qs | qt) = W1s (input-major, 8 x 64), qp[0..63] = t1
             qs[k] = OQ.g.w1s[k], qt[k] = OQ.g.w1s[256 + k];
@@ -1036,14 +1038,20 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
         constexpr int kQItems = (32 * kQVec + kProdThreads - 1) / kProdThreads;
         constexpr int PD = (N > 128) ? 1 : 2;           // k-blocks of loads in flight per thread (register ring, no spills)
         constexpr int kPVec = MV / 4;                   // valid float4 per P row
-        constexpr int kPItems = 32 * kPVec / kProdThreads;   // float4 of the P slab per thread
+        constexpr bool kGram = PMODE == 6;
+        static_assert(!kGram || (N == 64 && MV == 64), "Gram mode: 64 x 64");
+        constexpr int kPItems = kGram ? 1 : 32 * kPVec / kProdThreads;   // float4 of the P slab per thread (Gram: none, ring unused)
         RawVec pv[PD][kPItems], qv[PD][kQItems];
         if (MV < 128) {   // channels MV..127 of every P tile (hi and lo, all stages) stay zero for the whole kernel
             constexpr int kZero = (4 - MV / 32) * 4096;
             for (int s2 = 0; s2 < kStages; ++s2)
                 for (int t = 0; t < 2; ++t) {
                     uint8_t *zb = smem + s2 * SM::kStageBytes + t * SM::kPBytes + (MV / 32) * 4096;
-                    for (int o = tid * 16; o < kZero; o += kProdThreads * 16) *reinterpret_cast<float4 *>(zb + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int o = tid * 16; o < kZero; o += kProdThreads * 16) {
+                        // Gram: channel 64 (first float of 32-byte chunk (line & 3) of every line of chunk 2) of the hi tile = 1
+                        const bool one = kGram && t == 0 && o < 4096 && (o & 127) == (((o >> 7) & 3) << 5);
+                        *reinterpret_cast<float4 *>(zb + o) = make_float4(one ? 1.f : 0.f, 0.f, 0.f, 0.f);
+                    }
                 }
         }
         // Q gathered on the fly (modes 4 / 5): qd[i].arg carries the neighbour index of the row this ring slot gathers
@@ -1056,10 +1064,12 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
         auto issue = [&](long long kbk, RawVec (&pd)[kPItems], RawVec (&qd)[kQItems]) {
             if (kbk < nkb_total && !SG4D_DBG(p.dbg_no_load)) {
                 const long long row_base = t_beg * kTileM + kbk * kKB;
+                if constexpr (!kGram) {
 #pragma unroll
-                for (int i = 0; i < kPItems; ++i) {
-                    const int item = tid + kProdThreads * i;
-                    op_load<PMODE>(OP, row_base + item / kPVec, p.R, 4 * (item % kPVec), pd[i]);
+                    for (int i = 0; i < kPItems; ++i) {
+                        const int item = tid + kProdThreads * i;
+                        op_load<PMODE>(OP, row_base + item / kPVec, p.R, 4 * (item % kPVec), pd[i]);
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < kQItems; ++i) {
@@ -1100,11 +1110,13 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
                     const int stage = (int)(kbk % kStages);
                     mbar_wait_warp<40>(lane, bar_empty + 8 * stage, (uint32_t)(((kbk / kStages) & 1) ^ 1));
                     uint8_t *st = smem + stage * SM::kStageBytes;
+                    uint8_t *stq = kGram ? st : st + 2 * SM::kPBytes;                       // where the Q operand goes
+                    constexpr int kQLo = kGram ? SM::kPBytes : SM::kQBytes;                 // hi -> lo tile distance
 #pragma unroll
-                    for (int i = 0; i < kPItems; ++i) {
+                    for (int i = 0; i < (kGram ? 0 : kPItems); ++i) {
                         const int item = tid + kProdThreads * i;
                         const int r = item / kPVec, pc4 = item % kPVec;
-                        const float4 v = op_apply<PMODE>(OP, pv[j][i], row_base + r, p.R, 4 * pc4, ps, pt, pp);
+                        const float4 v = op_apply<(kGram ? 0 : PMODE)>(OP, pv[j][i], row_base + r, p.R, 4 * pc4, ps, pt, pp);
                         const uint32_t off = mn_b32_offset(r, pc4);
                         if constexpr (LP) {
                             *reinterpret_cast<float4 *>(st + off) = bf16_round4(v);
@@ -1133,12 +1145,12 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
                             }
                             const uint32_t off = mn_b32_offset(r, c4);
                             if constexpr (LP) {
-                                *reinterpret_cast<float4 *>(st + 2 * SM::kPBytes + off) = bf16_round4(v);
+                                *reinterpret_cast<float4 *>(stq + off) = bf16_round4(v);
                             } else {
                                 float4 hi, lo;
                                 split4_rn(v, hi, lo);
-                                *reinterpret_cast<float4 *>(st + 2 * SM::kPBytes + off) = hi;
-                                *reinterpret_cast<float4 *>(st + 2 * SM::kPBytes + SM::kQBytes + off) = lo;
+                                *reinterpret_cast<float4 *>(stq + off) = hi;
+                                *reinterpret_cast<float4 *>(stq + kQLo + off) = lo;
                             }
                         }
                     }
@@ -1165,7 +1177,7 @@ __global__ void __launch_bounds__(kMlpThreadsT2, 1) wgrad_kernel(WgradArgs p) {
             if (lane == 0) {
                 const uint32_t d_tmem = tmem + (uint32_t)(buf * kTmemCols);
                 const uint32_t p_hi = smem_base + stage * SM::kStageBytes, p_lo = p_hi + SM::kPBytes;
-                const uint32_t q_hi = p_hi + 2 * SM::kPBytes, q_lo = q_hi + SM::kQBytes;
+                const uint32_t q_hi = PMODE == 6 ? p_hi : p_hi + 2 * SM::kPBytes, q_lo = PMODE == 6 ? p_lo : q_hi + SM::kQBytes;
 #pragma unroll
                 for (int ks = 0; ks < kKB / 8 && !SG4D_DBG(p.dbg_no_mma); ++ks) {   // 8 rows = one 1024-byte atom per chunk
                     const uint32_t ko = ks * p.d_kstep;
@@ -1375,8 +1387,9 @@ static int launch_wgrad(const WgradArgs &a0, int grid, cudaStream_t stream, int 
     a.dbg_no_mma = no_mma, a.dbg_no_load = no_load;
 #endif
     a.lp = g_precision;
+    constexpr int kWide = PM == 6 ? 64 : 128;   // Gram mode exists for 64 channels only
     auto kern = (a.P.ncols <= 64 && blocks == 1) ? (a.lp ? wgrad_kernel<N, PM, QM, 64, true> : wgrad_kernel<N, PM, QM, 64, false>)
-                                                  : (a.lp ? wgrad_kernel<N, PM, QM, 128, true> : wgrad_kernel<N, PM, QM, 128, false>);
+                                                  : (a.lp ? wgrad_kernel<N, PM, QM, kWide, true> : wgrad_kernel<N, PM, QM, kWide, false>);
     const int smem = WgSmem<N>::total(PM);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return status_of(e);
@@ -1758,6 +1771,146 @@ extern "C" int sg4d_sa1_bwd_dw2(long long rows, int n, int m, int ns, int pstrid
     const int st = launch_wgrad<64, 2, 4>(args, grid, (cudaStream_t)stream);
     if (st != SG4D_OK) return st;
     wgrad_reduce_kernel<<<(n2 * 64 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(grid, n2, 64, 64, partial, dw2, 64);
+    return SG4D_LAUNCH_CHECK();
+}
+
+// ---- SA1 second-layer weight gradient without the dY2 operand -----------------------------------------------------------
+// dY2[r, c] = [garg(g, c) == slot(r)] dsel(g, c) - (a2[c] y2[r, c] + b2[c])  and  y2 = W2 h1  (h1 = relu(W1s x + t1)), hence
+//     dW2 = dY2^T h1 = T1 - diag(a2) W2 M - b2 (x) s,      M = h1^T h1 (64 x 64),  s = column sums of h1,
+//     T1[c, :] = sum over groups g of dsel(g, c) h1[row of g that won channel c, :].
+// M and s come from ONE 64-wide operand (wgrad_kernel in Gram mode: a third of the operand work of the dY2^T h1 form and no
+// read of y2); T1 touches one row per (group, channel) and runs on the CUDA cores (sa1_t1_kernel); sa1_dw2_combine_kernel
+// adds the three terms in fp64.
+namespace sg4d {
+
+constexpr int kT1Grid = SG4D_NUM_SMS * 2;
+
+template <int N2>
+__global__ void __launch_bounds__(256, 2)
+sa1_t1_kernel(GroupSrc g, long long R, const float *__restrict__ dsel, const uint8_t *__restrict__ garg, float *__restrict__ partial) {
+    constexpr int kHS = 68;                         // row stride of the h1 tile (floats): 16-byte aligned, spreads the banks
+    constexpr int kParts = 256 / N2, kW = 64 / kParts;   // thread (c, part) owns T1[c, part * kW .. + kW)
+    __shared__ __align__(16) float w_s[8 * 64];
+    __shared__ __align__(16) float t_s[64];
+    __shared__ __align__(16) float xs[kTileM][8];
+    __shared__ __align__(16) float hs[kTileM * kHS];
+    const int tid = threadIdx.x;
+    for (int k = tid; k < 512; k += 256) w_s[k] = g.w1s[k];
+    if (tid < 64) t_s[tid] = g.t1[tid];
+    const int ns = 1 << g.logns, gpt = kTileM >> g.logns;     // groups per tile
+    const long long ntiles = (R + kTileM - 1) / kTileM, groups = R >> g.logns;
+    const int c = tid % N2, kbase = (tid / N2) * kW;
+    float acc[kW];
+#pragma unroll
+    for (int j = 0; j < kW; ++j) acc[j] = 0.f;
+    int ixn = 0;                                    // neighbour index of my row of the NEXT tile (gather threads)
+    if (tid < kTileM) {
+        const long long row = (long long)blockIdx.x * kTileM + tid;
+        ixn = row < R ? __ldg(g.idx + row) : 0;
+    }
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();                            // the previous tile's hs / xs are no longer read (and w_s / t_s are written)
+        if (tid < kTileM) {
+            const long long row = tile * kTileM + tid;
+            float x[8];
+            sa1_gather_row(g, row, row < R, ixn, x);
+            const long long rown = row + (long long)gridDim.x * kTileM;
+            ixn = rown < R ? __ldg(g.idx + rown) : 0;
+            *reinterpret_cast<float4 *>(&xs[tid][0]) = make_float4(x[0], x[1], x[2], x[3]);
+            *reinterpret_cast<float4 *>(&xs[tid][4]) = make_float4(x[4], x[5], x[6], x[7]);
+        }
+        // the first 8 groups' (dsel, winner) of my channel: in flight while h1 is computed
+        float dv[8];
+        int av[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const long long gi = tile * gpt + q;
+            const bool ok = q < gpt && gi < groups;
+            dv[q] = ok ? __ldg(dsel + gi * N2 + c) : 0.f;
+            av[q] = ok ? (int)__ldg(garg + gi * N2 + c) : 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kTileM * 16 / 256; ++i) {
+            const int item = tid + 256 * i, r = item >> 4, c4 = item & 15;
+            const float4 xa = *reinterpret_cast<const float4 *>(&xs[r][0]), xb = *reinterpret_cast<const float4 *>(&xs[r][4]);
+            const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            float4 v = sa1_y1bn_smem(x, w_s, 4 * c4, *reinterpret_cast<const float4 *>(t_s + 4 * c4));
+            v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+            *reinterpret_cast<float4 *>(hs + r * kHS + 4 * c4) = v;     // (rows >= R are never selected below)
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (q < gpt) {                          // (dv = 0 beyond the last group)
+                const float *h = hs + (q * ns + av[q]) * kHS + kbase;
+#pragma unroll
+                for (int j = 0; j < kW; j += 4) {
+                    const float4 hv = *reinterpret_cast<const float4 *>(h + j);
+                    acc[j] = fmaf(dv[q], hv.x, acc[j]), acc[j + 1] = fmaf(dv[q], hv.y, acc[j + 1]);
+                    acc[j + 2] = fmaf(dv[q], hv.z, acc[j + 2]), acc[j + 3] = fmaf(dv[q], hv.w, acc[j + 3]);
+                }
+            }
+        }
+        for (int gl = 8; gl < gpt; ++gl) {          // nsample 8: groups 8..15 of the tile
+            const long long gi = tile * gpt + gl;
+            if (gi >= groups) break;
+            const float d = __ldg(dsel + gi * N2 + c);
+            const float *h = hs + (gl * ns + (int)__ldg(garg + gi * N2 + c)) * kHS + kbase;
+#pragma unroll
+            for (int j = 0; j < kW; j += 4) {
+                const float4 hv = *reinterpret_cast<const float4 *>(h + j);
+                acc[j] = fmaf(d, hv.x, acc[j]), acc[j + 1] = fmaf(d, hv.y, acc[j + 1]);
+                acc[j + 2] = fmaf(d, hv.z, acc[j + 2]), acc[j + 3] = fmaf(d, hv.w, acc[j + 3]);
+            }
+        }
+    }
+    float *out = partial + ((size_t)blockIdx.x * N2 + c) * 64 + kbase;
+#pragma unroll
+    for (int j = 0; j < kW; j += 4) *reinterpret_cast<float4 *>(out + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+}
+
+// dW2[c, k] = sum_parts T1 - a2[c] sum_j W2[c, j] M[j, k] - b2[c] s[k];  mh (65, 64): rows 0..63 = M, row 64 = s
+__global__ void __launch_bounds__(256)
+sa1_dw2_combine_kernel(int n2, int nparts, const float *__restrict__ t1part, const float *__restrict__ mh,
+                       const float *__restrict__ w2, const float *__restrict__ a2, const float *__restrict__ b2,
+                       float *__restrict__ dw2) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= n2 * 64) return;
+    const int c = t >> 6, k = t & 63;
+    double acc = 0.0;
+    for (int q = 0; q < nparts; ++q) acc += (double)t1part[((size_t)q * n2 + c) * 64 + k];
+    double wm = 0.0;
+    for (int j = 0; j < 64; ++j) wm += (double)w2[c * 64 + j] * (double)mh[j * 64 + k];
+    dw2[t] = (float)(acc - (double)a2[c] * wm - (double)b2[c] * (double)mh[64 * 64 + k]);
+}
+
+}  // namespace sg4d
+
+extern "C" long long sg4d_sa1_bwd_dw2_gram_ws_floats(long long rows, int n2) {
+    return (long long)mlp_grid(rows) * kTileM * 64 + 65 * 64 + (long long)kT1Grid * n2 * 64;
+}
+
+extern "C" int sg4d_sa1_bwd_dw2_gram(long long rows, int n, int m, int ns, int pstride, int fstride, int foff, int c,
+                                     const float *pts, const float *feats, const float *centers, const int32_t *idx,
+                                     const float *w1s, const float *t1, int n2, const float *w2, const float *a2, const float *b2,
+                                     const float *dsel, const uint8_t *garg, float *ws, float *dw2, sg4d_stream_t stream) {
+    WgradArgs args{};
+    if (!fill_src(args.Q.g, rows, n, m, ns, pstride, fstride, foff, c, pts, feats, centers, idx) || c > 4 || !w1s || !t1 ||
+        (n2 != 64 && n2 != 128) || !w2 || !a2 || !b2 || !dsel || !garg || !ws || !dw2 || ns < 8)
+        return SG4D_EINVAL;
+    args.Q.g.w1s = w1s, args.Q.g.t1 = t1, args.Q.ncols = 64, args.P.ncols = 64;
+    const int grid = mlp_grid(rows);
+    float *gram_part = ws, *mh = ws + (size_t)grid * kTileM * 64, *t1part = mh + 65 * 64;
+    args.R = rows, args.partial = gram_part;
+    args.d_lbo = 4096, args.d_sbo = 512, args.d_type = 1, args.d_kstep = 1024;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_wgrad<64, 6, 4>(args, grid, st);
+    if (rc != SG4D_OK) return rc;
+    wgrad_reduce_kernel<<<(65 * 64 + 255) / 256, 256, 0, st>>>(grid, 65, 64, 64, gram_part, mh, 64);
+    if (n2 == 64) sa1_t1_kernel<64><<<kT1Grid, 256, 0, st>>>(args.Q.g, rows, dsel, garg, t1part);
+    else sa1_t1_kernel<128><<<kT1Grid, 256, 0, st>>>(args.Q.g, rows, dsel, garg, t1part);
+    sa1_dw2_combine_kernel<<<(n2 * 64 + 255) / 256, 256, 0, st>>>(n2, kT1Grid, t1part, mh, w2, a2, b2, dw2);
     return SG4D_LAUNCH_CHECK();
 }
 

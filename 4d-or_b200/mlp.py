@@ -281,9 +281,11 @@ class _FusedSA1(torch.autograd.Function):
         s1part = torch.empty(lib.sg4d_sa1_s1part_doubles(rows), dtype=torch.float64, device=dev)
         _lib.call("sg4d_sa1_bwd_da", pts, *src, w1s.data_ptr(), t1.data_ptr(), n2, y2.data_ptr(), a2.data_ptr(), b2.data_ptr(),
                   dsel.data_ptr(), garg.data_ptr(), pack_weight(w2.t()).data_ptr(), s1part.data_ptr())
+        # dW2 = dY2^T h1 without the dY2 operand: T1 - diag(a2) W2 (h1^T h1) - b2 (x) colsum(h1)  (include/sg4d.h)
         d_w2 = torch.empty(n2, 64, dtype=torch.float32, device=dev)
-        _lib.call("sg4d_sa1_bwd_dw2", pts, *src, w1s.data_ptr(), t1.data_ptr(), n2, y2.data_ptr(), a2.data_ptr(), b2.data_ptr(),
-                  dsel.data_ptr(), garg.data_ptr(), _wgrad_partial(rows, 64, dev).data_ptr(), d_w2.data_ptr())
+        ws = torch.empty(lib.sg4d_sa1_bwd_dw2_gram_ws_floats(rows, n2), dtype=torch.float32, device=dev)
+        _lib.call("sg4d_sa1_bwd_dw2_gram", pts, *src, w1s.data_ptr(), t1.data_ptr(), n2, w2.contiguous().data_ptr(), a2.data_ptr(),
+                  b2.data_ptr(), dsel.data_ptr(), garg.data_ptr(), ws.data_ptr(), d_w2.data_ptr())
         d_w1 = torch.empty(64, k, dtype=torch.float32, device=dev)
         d_gb1 = torch.empty(2, 64, dtype=torch.float32, device=dev)
         _lib.call("sg4d_sa1_bwd_finalize", pts, k, rows, s1part.data_ptr(), moments.data_ptr(), w1.data_ptr(), k,

@@ -513,6 +513,11 @@ def main_sg4d(args):
             return a[0] * 4 * (2 * a[1] + a[2]), 2 * a[0] * a[1] * a[2]
         if nm == "sg4d_inner_bwd_dw":            # (rows, C1, k, ldx)
             return a[0] * 4 * (2 * a[1] + a[2]), 2 * a[0] * a[1] * a[2]
+        if nm == "sg4d_sa1_bwd_dw2_gram":        # Gram kernel + T1 kernel: each reads idx and the gathered points; T1 also dsel / garg
+            rows, n_, m_, ns_, ps_, fs_ = a[:6]
+            n2 = a[-1]
+            cloud_bytes = min((rows // (m_ * ns_)) * n_, rows) * ps_ * 4
+            return 2 * (rows * 4 + cloud_bytes) + (rows // ns_) * n2 * 5, 2 * rows * 64 * n2
         if nm in ("sg4d_sa1_fwd", "sg4d_sa1_bwd_da", "sg4d_sa1_bwd_dw2", "sg4d_sa_moments"):
             rows, n_, m_, ns_, ps_, fs_ = a[:6]       # then [foff,] c, n2 (zero-valued arguments are not recorded)
             n2 = a[-1] if nm != "sg4d_sa_moments" else 0
@@ -556,8 +561,8 @@ def main_sg4d(args):
     #      algorithmic bytes of all its launches / their summed duration (= bytes per launch / average launch duration)
     row_calls = ("sg4d_linear_fwd", "sg4d_pool_bwd_da", "sg4d_inner_bwd_dx", "sg4d_sa1_fwd", "sg4d_sa1_bwd_da",
                  "sg4d_linear_fwd_grouped", "sg4d_dense_fwd", "sg4d_dense_bwd_dx")
-    wg_calls = ("sg4d_pool_bwd_dw", "sg4d_inner_bwd_dw", "sg4d_sa1_bwd_dw2", "sg4d_inner_bwd_dw_grouped", "sg4d_dense_bwd_dw",
-                "sg4d_dense_pool_bwd_dw")
+    wg_calls = ("sg4d_pool_bwd_dw", "sg4d_inner_bwd_dw", "sg4d_sa1_bwd_dw2", "sg4d_sa1_bwd_dw2_gram", "sg4d_inner_bwd_dw_grouped",
+                "sg4d_dense_bwd_dw", "sg4d_dense_pool_bwd_dw")
     family = {c: "row_gemm_kernel" for c in row_calls}
     family.update({c: "wgrad_kernel" for c in wg_calls})
     family.update({"sg4d_fps_indexed": "fps_indexed_kernel", "sg4d_fps_rows": "fps_onchip_kernel",

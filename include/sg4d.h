@@ -332,6 +332,15 @@ int sg4d_sa1_bwd_dw2(long long rows, int n, int m, int ns, int pstride, int fstr
                      const float *feats, const float *centers, const int32_t *idx, const float *w1s, const float *t1,
                      int n2, const float *y2, const float *a2, const float *b2, const float *dsel, const uint8_t *garg,
                      float *partial, float *dw2, sg4d_stream_t stream);
+/* Same result as sg4d_sa1_bwd_dw2 without reading y2: dY2 = [winner] dsel - (a2 y2 + b2) and y2 = W2 h1 give
+ *   dW2 = T1 - diag(a2) W2 (h1^T h1) - b2 (x) colsum(h1),   T1[c, :] = sum_g dsel(g, c) h1[winning row of (g, c), :];
+ * the Gram matrix comes from one 64-wide tensor-core operand, T1 from one row per (group, channel).  w2 (n2, 64) row-major;
+ * ws: sg4d_sa1_bwd_dw2_gram_ws_floats(rows, n2) floats of scratch. */
+long long sg4d_sa1_bwd_dw2_gram_ws_floats(long long rows, int n2);
+int sg4d_sa1_bwd_dw2_gram(long long rows, int n, int m, int ns, int pstride, int fstride, int foff, int c,
+                          const float *pts, const float *feats, const float *centers, const int32_t *idx,
+                          const float *w1s, const float *t1, int n2, const float *w2, const float *a2, const float *b2,
+                          const float *dsel, const uint8_t *garg, float *ws, float *dw2, sg4d_stream_t stream);
 /* d_beta1 = S1[:, 7];  d_gamma1 = i1 .* (sum_j W1 .* S1 - m1 .* d_beta1);  dW1 (64 x k, row stride lddw) =
  * p1 .* S1 - q1 .* (W1 M) - u1 (x) M[:, 7]  (BatchNorm backward, linear in S1 and M; q1 = u1 = 0 unless batch_stats) */
 int sg4d_sa1_bwd_finalize(int k, long long rows, const double *s1part, const double *moments, const float *w1, int ldw,
