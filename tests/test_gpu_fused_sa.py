@@ -120,3 +120,39 @@ def test_linearity_kernels_match_torch(cuda, b, n, m, ns, c1, seed):
               u1.data_ptr(), di.data_ptr(), dn.data_ptr(), gs.data_ptr())
     want_g = torch.zeros(b * n, c1, dtype=torch.float64, device=cuda).index_add_(0, flat, dy)
     torch.testing.assert_close(gs.double(), want_g, rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("b,n,m,ns,c_pts,n2,seed", [(2, 900, 96, 16, 4, 64, 21), (2, 700, 50, 32, 3, 128, 22), (1, 400, 9, 128, 4, 128, 23)])
+def test_sa1_dw2_gram_form_equals_operand_form(cuda, b, n, m, ns, c_pts, n2, seed):
+    """sg4d_sa1_bwd_dw2_gram (T1 - diag(a2) W2 h1^T h1 - b2 (x) colsum h1) against sg4d_sa1_bwd_dw2 (dY2^T h1 with the dY2 operand
+    built from y2) on the same saved tensors and arbitrary dsel / a2 / b2"""
+    from sg4d import _lib, mlp
+    pts, _, centers, idx, cnt = _scene(b, n, m, ns, c_pts, 0, seed)
+    net = _mlp(3 + c_pts, 64, n2, seed).to(cuda).train()
+    dp, dc, di, dn = pts.to(cuda), centers.to(cuda), idx.to(cuda), cnt.to(cuda)
+    mlp.CAPTURE = []
+    try:
+        with torch.no_grad():
+            mlp.fused_sa_scale("sa1", dp, dp, 3, c_pts, dc, di, dn, net)
+        cap = [c for c in mlp.CAPTURE if c.get("kind") == "sa1" and "y2" in c][0]
+    finally:
+        mlp.CAPTURE = None
+    g = torch.Generator().manual_seed(seed)
+    groups = b * m
+    dsel = torch.randn(groups, n2, generator=g).to(cuda)
+    a2, b2 = (1e-3 * torch.randn(n2, generator=g)).to(cuda), (1e-3 * torch.randn(n2, generator=g)).to(cuda)
+    src = mlp._src_args(dp, None, 3, c_pts, dc, di)
+    rows = src[0]
+    w2 = net[3].weight.detach().view(n2, 64).contiguous()
+    t1 = cap["stats1"][1].contiguous()
+    lib = _lib.load()
+    want = torch.empty(n2, 64, device=cuda)
+    _lib.call("sg4d_sa1_bwd_dw2", dp, *src, cap["w1s"].data_ptr(), t1.data_ptr(), n2, cap["y2"].data_ptr(), a2.data_ptr(), b2.data_ptr(),
+              dsel.data_ptr(), cap["garg"].data_ptr(), mlp._wgrad_partial(rows, 64, cuda).data_ptr(), want.data_ptr())
+    got = torch.empty(n2, 64, device=cuda)
+    ws = torch.empty(lib.sg4d_sa1_bwd_dw2_gram_ws_floats(rows, n2), device=cuda)
+    _lib.call("sg4d_sa1_bwd_dw2_gram", dp, *src, cap["w1s"].data_ptr(), t1.data_ptr(), n2, w2.data_ptr(), a2.data_ptr(), b2.data_ptr(),
+              dsel.data_ptr(), cap["garg"].data_ptr(), ws.data_ptr(), got.data_ptr())
+    err = float((got - want).double().norm() / want.double().norm())
+    assert err < 1e-5, err
+    assert float((got - want).abs().max() / want.abs().max()) < 1e-5
