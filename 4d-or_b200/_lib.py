@@ -50,6 +50,7 @@ SIGNATURES = {
     "sg4d_inner_bwd_dw": [_i64, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "sg4d_pool_bwd_prologue": [_i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "sg4d_partial_sums": [_i, _i, _p, _p, _p],
+    "sg4d_bn_bwd_coeffs": [_i, _i64, _i, _p, _p, _p, _p, _p, _p, _p],
     "sg4d_sa_moments": [_i64] + [_i] * 7 + [_p] * 5 + [_p],
     "sg4d_sa1_bn1": [_i, _i, _p, _p, _i, _p, _p, _f, _f, _p, _p, _i, _p, _p, _p, _p],
     "sg4d_sa1_fwd": [_i64] + [_i] * 7 + [_p] * 6 + [_i] + [_p] * 6 + [_p],

@@ -452,11 +452,20 @@ gather_y1_kernel(long long rows, int n, int m, int nsample, int c1, const float 
             since = 0;
         }
     }
+    // one pair per (block, channel): the row lanes of a block are folded in a fixed order through shared memory
+    __shared__ double red[256][8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const size_t i = ((size_t)blockIdx.x * lanes + rl) * c1 + 4 * cg + u;
-        partial[2 * i] = ds[u] + (double)s[u];
-        partial[2 * i + 1] = dq[u] + (double)q[u];
+    for (int u = 0; u < 4; ++u) red[threadIdx.x][2 * u] = ds[u] + (double)s[u], red[threadIdx.x][2 * u + 1] = dq[u] + (double)q[u];
+    __syncthreads();
+    if (rl == 0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            double a = 0.0, b = 0.0;
+            for (int l = 0; l < lanes; ++l) a += red[l * vec + cg][2 * u], b += red[l * vec + cg][2 * u + 1];
+            const size_t i = (size_t)blockIdx.x * c1 + 4 * cg + u;
+            partial[2 * i] = a;
+            partial[2 * i + 1] = b;
+        }
     }
 }
 
@@ -494,7 +503,7 @@ group_sum_dy_kernel(long long groups, int nsample, int c1, const float *__restri
 
 }  // namespace sg4d
 
-extern "C" int sg4d_gather_y1_parts(int c1) { return SG4D_NUM_SMS * 8 * (256 / (c1 >> 2)) * c1; }   // fp64 PAIRS
+extern "C" int sg4d_gather_y1_parts(int c1) { return SG4D_NUM_SMS * 8 * c1; }   // fp64 PAIRS: one per (block, channel)
 
 extern "C" int sg4d_gather_y1(long long rows, int n, int m, int nsample, int c1, const float *z, const float *cc,
                               const int32_t *idx, float *y1, double *partial, sg4d_stream_t stream) {

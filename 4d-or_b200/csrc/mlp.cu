@@ -1558,6 +1558,30 @@ extern "C" int sg4d_pool_bwd_prologue(long long groups, int n, int ldd, const fl
     return SG4D_LAUNCH_CHECK();
 }
 
+// BatchNorm-backward coefficients of one layer from its two per-channel sums (d_beta = sum dz, d_gamma = sum dz xhat):
+//   coef[0] = q = scale d_gamma invstd / rows,  coef[1] = u = scale d_beta / rows - q mean   (both 0 without batch statistics),
+//   coef[2] = -mean invstd.   dY = p dz - (q y + u) with p = scale.  One launch instead of a dozen per-channel ATen kernels.
+__global__ void bn_bwd_coeffs_kernel(int n, long long rows, int batch_stats, const float *__restrict__ d_beta,
+                                     const float *__restrict__ d_gamma, const float *__restrict__ scale,
+                                     const float *__restrict__ mean, const float *__restrict__ invstd, float *__restrict__ coef) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const float inv_r = 1.0f / (float)rows;
+    float q = 0.f, u = 0.f;
+    if (batch_stats) {
+        q = scale[c] * d_gamma[c] * invstd[c] * inv_r;
+        u = scale[c] * d_beta[c] * inv_r - q * mean[c];
+    }
+    coef[c] = q, coef[n + c] = u, coef[2 * n + c] = -mean[c] * invstd[c];
+}
+
+extern "C" int sg4d_bn_bwd_coeffs(int n, long long rows, int batch_stats, const float *d_beta, const float *d_gamma,
+                                  const float *scale, const float *mean, const float *invstd, float *coef, sg4d_stream_t stream) {
+    if (n <= 0 || rows <= 0 || !d_beta || !d_gamma || !scale || !mean || !invstd || !coef) return SG4D_EINVAL;
+    bn_bwd_coeffs_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, rows, batch_stats, d_beta, d_gamma, scale, mean, invstd, coef);
+    return SG4D_LAUNCH_CHECK();
+}
+
 extern "C" int sg4d_partial_sums(int n, int nparts, const double *partial, float *out, sg4d_stream_t stream) {
     if (n <= 0 || nparts <= 0 || !partial || !out) return SG4D_EINVAL;
     partial_sum_kernel<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(n, nparts, partial, out);

@@ -194,11 +194,7 @@ class _LinearBNReLU(torch.autograd.Function):
                   dzs.data_ptr(), n, part.data_ptr(), sums.data_ptr())
         d_beta, d_gamma = sums[0], sums[1]
         s, m, i = stats[0], stats[2], stats[3]
-        if batch:
-            q1 = s * d_gamma * i * (1.0 / rows)
-            u1 = s * d_beta * (1.0 / rows) - q1 * m
-        else:
-            q1, u1 = torch.zeros_like(s), torch.zeros_like(s)
+        q1, u1, _ = fused.bn_bwd_coeffs(s, m, i, d_beta, d_gamma, rows, batch)
         p1 = torch.ones_like(s)
         dx = dw = None
         if ctx.needs_input_grad[0]:
@@ -279,11 +275,7 @@ class _DensePooledMLP(torch.autograd.Function):
         _lib.call("sg4d_dense_pool_bwd_dw", x, rows, n2, n1, group, y2.data_ptr(), a2.data_ptr(), b2.data_ptr(), dsel.data_ptr(),
                   garg.data_ptr(), y1.data_ptr(), s1.data_ptr(), t1.data_ptr(), wpart.data_ptr(), d_w2.data_ptr())
         p1 = s1.contiguous()
-        if batch1:
-            q1 = s1 * d_g1 * i1 * (1.0 / rows)
-            u1 = s1 * d_be1 * (1.0 / rows) - q1 * m1
-        else:
-            q1, u1 = torch.zeros_like(s1), torch.zeros_like(s1)
+        q1, u1, _ = fused.bn_bwd_coeffs(s1, m1, i1, d_be1.contiguous(), d_g1.contiguous(), rows, batch1)
         d_w1 = _dw(rows, n1, y1, 3, x, kp, a2=dz1, p1=p1, q1=q1, u1=u1)
         d_x = None
         if ctx.needs_input_grad[0]:

@@ -93,6 +93,15 @@ def supported(mlp, k_padded, group):
     return True
 
 
+def bn_bwd_coeffs(scale, mean, invstd, d_beta, d_gamma, rows, batch):
+    """(q, u, -mean * invstd) of the BatchNorm backward  dY = scale * dz - (q * y + u)  in one launch (sg4d_bn_bwd_coeffs)."""
+    n = scale.numel()
+    coef = torch.empty(3, n, dtype=torch.float32, device=scale.device)
+    _lib.call("sg4d_bn_bwd_coeffs", scale, n, rows, 1 if batch else 0, d_beta.data_ptr(), d_gamma.data_ptr(), scale.data_ptr(),
+              mean.data_ptr(), invstd.data_ptr(), coef.data_ptr())
+    return coef[0], coef[1], coef[2]
+
+
 def _wgrad_partial(rows, npad, dev):
     return torch.empty(_lib.load().sg4d_wgrad_partial_floats(rows, npad), dtype=torch.float32, device=dev)
 
@@ -138,12 +147,7 @@ class _FusedSharedMLP(torch.autograd.Function):
         sums2 = torch.empty(2, n2, dtype=torch.float32, device=dev)
         _lib.call("sg4d_partial_sums", x, n2, nparts, part2.data_ptr(), sums2.data_ptr())
         d_be2, d_g2 = sums2[0], sums2[1]
-        if batch2:
-            a2 = s2 * d_g2 * i2 * inv_r
-            b2 = s2 * d_be2 * inv_r - a2 * m2
-        else:
-            a2 = torch.zeros_like(s2)
-            b2 = torch.zeros_like(s2)
+        a2, b2, _ = bn_bwd_coeffs(s2, m2, i2, d_be2, d_g2, rows, batch2)
         em1 = (-m1 * i1).contiguous()
         dz1 = torch.empty(rows, n1, dtype=torch.float32, device=dev)
         part = torch.empty(_lib.load().sg4d_mlp_partial_doubles(rows), dtype=torch.float64, device=dev)
@@ -160,12 +164,7 @@ class _FusedSharedMLP(torch.autograd.Function):
 
         # ---- layer 1: dY1 = p1*dz1 - (q1*y1 + u1)
         p1 = s1.contiguous()
-        if batch1:
-            q1 = s1 * d_g1 * i1 * inv_r
-            u1 = s1 * d_be1 * inv_r - q1 * m1
-        else:
-            q1 = torch.zeros_like(s1)
-            u1 = torch.zeros_like(s1)
+        q1, u1, _ = bn_bwd_coeffs(s1, m1, i1, d_be1, d_g1, rows, batch1)
         npad = 32 if kp <= 32 else (64 if kp <= 64 else (128 if kp <= 128 else 224))
         d_w1 = torch.empty(n1, kp, dtype=torch.float32, device=dev)
         _lib.call("sg4d_inner_bwd_dw", x, rows, n1, kp, kp, y1.data_ptr(), dz1.data_ptr(), p1.data_ptr(), q1.data_ptr(),
@@ -221,12 +220,7 @@ def _pool_bwd_consts(d_out, out, gsel, s2, m2, i2, rows, batch2, ref):
     sums2 = torch.empty(2, n2, dtype=torch.float32, device=dev)
     _lib.call("sg4d_partial_sums", ref, n2, nparts, part2.data_ptr(), sums2.data_ptr())
     d_be2, d_g2 = sums2[0], sums2[1]
-    if batch2:
-        a2 = s2 * d_g2 * i2 * (1.0 / rows)
-        b2 = s2 * d_be2 * (1.0 / rows) - a2 * m2
-    else:
-        a2 = torch.zeros_like(s2)
-        b2 = torch.zeros_like(s2)
+    a2, b2, _ = bn_bwd_coeffs(s2, m2, i2, d_be2, d_g2, rows, batch2)
     return dsel, a2, b2, d_g2, d_be2
 
 
@@ -353,12 +347,7 @@ class _FusedSA2(torch.autograd.Function):
                   garg.data_ptr(), y1.data_ptr(), s1.data_ptr(), t1.data_ptr(), _wgrad_partial(rows, n1, dev).data_ptr(),
                   d_w2.data_ptr())
         p1 = s1.contiguous()
-        if batch1:
-            q1 = s1 * d_g1 * i1 * (1.0 / rows)
-            u1 = s1 * d_be1 * (1.0 / rows) - q1 * m1
-        else:
-            q1 = torch.zeros_like(s1)
-            u1 = torch.zeros_like(s1)
+        q1, u1, _ = bn_bwd_coeffs(s1, m1, i1, d_be1, d_g1, rows, batch1)
         # dY1 = p1 .* dz1 - (q1 .* y1 + u1) is never stored: both sums below generate it on the fly
         g_sum = torch.empty(b * n, n1, dtype=torch.float32, device=dev)      # per source point (deterministic gather)
         _lib.call("sg4d_group_rows_grad_dy", xin, b, n, m, ns, n1, y1.data_ptr(), dz1.data_ptr(), p1.data_ptr(), q1.data_ptr(),

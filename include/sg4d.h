@@ -284,6 +284,10 @@ int sg4d_inner_bwd_dw(long long rows, int m, int k, int ldx, const float *y1, co
                       const float *q1, const float *u1, const float *x, float *partial, float *dw,
                       sg4d_stream_t stream);
 long long sg4d_wgrad_partial_floats(long long rows, int npad);
+/* BatchNorm-backward coefficients of one layer from its per-channel sums d_beta = sum dz, d_gamma = sum dz xhat:
+ * coef (3, n): q = scale d_gamma invstd / rows, u = scale d_beta / rows - q mean (both 0 unless batch_stats), -mean invstd. */
+int sg4d_bn_bwd_coeffs(int n, long long rows, int batch_stats, const float *d_beta, const float *d_gamma, const float *scale,
+                       const float *mean, const float *invstd, float *coef, sg4d_stream_t stream);
 /* out[0:n] = sum of the first, out[n:2n] = sum of the second component of the fp64 partial pairs */
 int sg4d_partial_sums(int n, int nparts, const double *partial, float *out, sg4d_stream_t stream);
 
