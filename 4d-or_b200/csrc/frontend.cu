@@ -146,7 +146,12 @@ fe_sample_kernel(FeSrc s, const int32_t *__restrict__ list, const int *__restric
                  float *__restrict__ dist) {
     const int c = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
     const int len = totals[c * tot_stride + 1];
-    const int i = j < N ? fe_pick(list, s.P, len, u, c, N, j) : -1;
+    // the draw (a dependent gather through the candidate list) is made once, in pass 0; passes 1 and 2 read it back coalesced
+    int i = -1;
+    if (j < N) {
+        if (PASS == 0) picked[(size_t)c * N + j] = i = fe_pick(list, s.P, len, u, c, N, j);
+        else i = picked[(size_t)c * N + j];
+    }
     const float *p = s.pts + (size_t)(i < 0 ? 0 : i) * s.stride;
     if (PASS == 0) {
         double sx = i >= 0 ? (double)p[0] : 0.0, sy = i >= 0 ? (double)p[1] : 0.0, sz = i >= 0 ? (double)p[2] : 0.0;
@@ -176,19 +181,29 @@ fe_sample_kernel(FeSrc s, const int32_t *__restrict__ list, const int *__restric
     // sqrt is monotone: max over rows of sqrt(n2) = sqrt(max n2) (:16)
     const float d = sqrtf(__uint_as_float(maxn2[c]));
     if (blockIdx.x == 0 && threadIdx.x == 0) dist[c] = d;
-    if (j >= N) return;
-    float *o = out + ((size_t)c * N + j) * fout;
-    if (i < 0) {
-        for (int a = 0; a < fout; ++a) o[a] = 0.f;
-    } else {
-        o[0] = __fdiv_rn(x, d), o[1] = __fdiv_rn(y, d), o[2] = __fdiv_rn(z, d);             // point /= furthest_distance (:17)
-        for (int a = 3; a < s.stride; ++a) o[a] = p[a];
-        if (edges) {      // 4th feature: 1 = point of the subject instance, 2 = of the object instance (:188-190)
-            const int m = s.masks[i];
-            o[s.stride] = m == (int)edges[c] + 1 ? 1.f : (m == (int)edges[E + c] + 1 ? 2.f : 0.f);
+    // rows of fout <= 8 floats are staged in shared memory and leave as consecutive 4-byte stores of the block's contiguous
+    // output range (a thread writing its own 6 / 7 floats would touch every 32-byte sector seven times)
+    __shared__ float so[256 * 8];
+    const bool staged = fout <= 8;
+    float *o = staged ? so + threadIdx.x * fout : out + ((size_t)c * N + j) * fout;
+    if (j < N) {
+        if (i < 0) {
+            for (int a = 0; a < fout; ++a) o[a] = 0.f;
+        } else {
+            o[0] = __fdiv_rn(x, d), o[1] = __fdiv_rn(y, d), o[2] = __fdiv_rn(z, d);             // point /= furthest_distance (:17)
+            for (int a = 3; a < s.stride; ++a) o[a] = p[a];
+            if (edges) {      // 4th feature: 1 = point of the subject instance, 2 = of the object instance (:188-190)
+                const int m = s.masks[i];
+                o[s.stride] = m == (int)edges[c] + 1 ? 1.f : (m == (int)edges[E + c] + 1 ? 2.f : 0.f);
+            }
         }
     }
-    if (picked) picked[(size_t)c * N + j] = i;
+    if (staged) {
+        __syncthreads();
+        const int j0 = blockIdx.x * 256, nvalid = min(256, N - j0) * fout;
+        float *dst = out + ((size_t)c * N + j0) * fout;
+        for (int t = threadIdx.x; t < nvalid; t += 256) dst[t] = so[t];
+    }
 }
 
 // centroid of every cloud: fp64 sum of the per-block partials in a fixed order (one warp per cloud), rounded once to fp32
@@ -254,7 +269,7 @@ extern "C" int sg4d_frontend_edges(int P, int stride, int E, const float *pts, c
 // Stage 3: draw n points per cloud from its list (u: (clouds, n) uniforms in [0,1)), gather [xyz | features | edge mask],
 // zero_mean.  edges == NULL: object clouds (fout = stride, totals = (nobj + 1), entry c + 1); else edge clouds
 // (fout = stride + 1, totals = (E, 2), entry [c][1]).  out (clouds, n, fout); picked (clouds, n) original indices or NULL;
-// mean (clouds, 3), dist (clouds); scratch: clouds * (ceil(n / 256) * 3 * 8 + 4) bytes.
+// mean (clouds, 3), dist (clouds); scratch: clouds * (ceil(n / 256) * 3 * 8 + 4 + 4 n) bytes.
 extern "C" int sg4d_frontend_sample(int P, int stride, int clouds, int n, const float *pts, const int32_t *masks,
                                     const int32_t *list, const int *totals, const int64_t *edges, const float *u, float *out,
                                     int32_t *picked, float *mean, float *dist, void *scratch, sg4d_stream_t stream) {
@@ -264,6 +279,7 @@ extern "C" int sg4d_frontend_sample(int P, int stride, int clouds, int n, const 
     const int nb = (n + 255) / 256, fout = stride + (edges ? 1 : 0);
     double *part = reinterpret_cast<double *>(scratch);
     unsigned *maxn2 = reinterpret_cast<unsigned *>(part + (size_t)clouds * nb * 3);
+    if (!picked) picked = reinterpret_cast<int32_t *>(maxn2 + clouds);     // the draws live in the scratch area
     cudaError_t e = cudaMemsetAsync(maxn2, 0, (size_t)clouds * 4, st);
     if (e != cudaSuccess) return status_of(e);
     FeSrc s{pts, masks, P, stride, nullptr};

@@ -12,8 +12,10 @@ from . import _lib, synthetic
 
 
 def prepare_scene(points, masks, n_obj, num_points, num_points_union, pairs="ordered", padding=0.2, u_obj=None, u_rel=None,
-                  generator=None, return_debug=False):
-    """points (P, S) float32 cuda, masks (P,) int32 cuda with values 0..n_obj.  Returns the batch dict (+ debug tensors)."""
+                  generator=None, return_debug=False, out_obj=None, out_rel=None):
+    """points (P, S) float32 cuda, masks (P,) int32 cuda with values 0..n_obj.  Returns the batch dict (+ debug tensors).
+    out_obj (n_obj, num_points, S) / out_rel (E, num_points_union, S + 1): optional contiguous destinations, e.g. this
+    scene's slices of a whole batch's tensors (no concatenation copy afterwards)."""
     _lib.require_cuda(points, masks)
     if points.dtype != torch.float32 or points.dim() != 2 or not points.is_contiguous() or masks.dtype != torch.int32:
         raise RuntimeError("points must be a contiguous (P, S) float tensor and masks an int32 tensor")
@@ -38,18 +40,21 @@ def prepare_scene(points, masks, n_obj, num_points, num_points_union, pairs="ord
     if u_rel is None:
         u_rel = torch.rand(E, num_points_union, device=dev, generator=generator)
 
-    def sample(clouds, n, lst, tot, e, u, fout):
-        out = torch.empty(clouds, n, fout, dtype=torch.float32, device=dev)
+    def sample(clouds, n, lst, tot, e, u, fout, out):
+        if out is None:
+            out = torch.empty(clouds, n, fout, dtype=torch.float32, device=dev)
+        elif out.shape != (clouds, n, fout) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dev:
+            raise RuntimeError(f"destination must be a contiguous float32 ({clouds}, {n}, {fout}) tensor on {dev}")
         picked = torch.empty(clouds, n, dtype=torch.int32, device=dev) if return_debug else None
         mean = torch.empty(clouds, 3, dtype=torch.float32, device=dev)
         dist = torch.empty(clouds, dtype=torch.float32, device=dev)
-        scratch = torch.empty(clouds * (((n + 255) // 256) * 6 + 1) + 2, dtype=torch.int32, device=dev)
+        scratch = torch.empty(clouds * (((n + 255) // 256) * 6 + 1 + n) + 2, dtype=torch.int32, device=dev)
         _lib.call("sg4d_frontend_sample", points, P, S, clouds, n, points.data_ptr(), masks.data_ptr(), lst.data_ptr(), tot.data_ptr(),
                   _lib.ptr(e), u.data_ptr(), out.data_ptr(), _lib.ptr(picked), mean.data_ptr(), dist.data_ptr(), scratch.data_ptr())
         return out, picked, mean, dist
 
-    obj, obj_pick, _, _ = sample(n_obj, num_points, obj_list, totals, None, u_obj.contiguous(), S)
-    rel, rel_pick, rel_mean, rel_dist = sample(E, num_points_union, edge_list, edge_totals, edges, u_rel.contiguous(), S + 1)
+    obj, obj_pick, _, _ = sample(n_obj, num_points, obj_list, totals, None, u_obj.contiguous(), S, out_obj)
+    rel, rel_pick, rel_mean, rel_dist = sample(E, num_points_union, edge_list, edge_totals, edges, u_rel.contiguous(), S + 1, out_rel)
     batch = {"obj_points": obj.permute(0, 2, 1), "rel_points": rel.permute(0, 2, 1), "edge_indices": edges}
     if return_debug:
         batch["_debug"] = {"obj_picked": obj_pick, "rel_picked": rel_pick, "obj_box": obj_box, "edge_box": edge_box,

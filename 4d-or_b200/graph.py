@@ -46,7 +46,9 @@ class GraphedStep:
                 if p.grad is not None:
                     p.grad.zero_()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # captured on a HIGH-priority stream: kernel nodes keep the capture stream's priority, so work queued beside the replay
+        # on ordinary streams (the next batch's upload / crop front-end) fills idle SMs instead of competing for them
+        with torch.cuda.graph(self.graph, stream=torch.cuda.Stream(device=dev, priority=-1)):
             if bucket is not None:
                 bucket.zero()
             else:

@@ -75,7 +75,7 @@ class SGPNModelWrapper(nn.Module):
         main = torch.cuda.current_stream(obj_points.device)
         side = self.__dict__.get('_side_stream')
         if side is None or side.device != obj_points.device:
-            side = torch.cuda.Stream(device=obj_points.device)
+            side = torch.cuda.Stream(device=obj_points.device, priority=-1)     # same priority as a graphed step's capture stream
             self.__dict__['_side_stream'] = side
         side.wait_stream(main)
         with torch.cuda.stream(side):

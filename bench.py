@@ -382,14 +382,22 @@ def main_sg4d(args):
     #      builds the 12 + 66 clouds of --points points per scene on the device -- the step immediately before the hot path
     #      in the reference (SGH/dataset/data_preparation_utils.py), there on the CPU.  --e2e-input crops uploads the
     #      pre-cropped clouds instead (171 MB per scene; round 1's path).
-    def timed_e2e(make_batch, h2d):
-        for _ in range(2):                      # untimed: allocations
-            step(make_batch(0))
+    def timed_e2e(make_batch, h2d, after_launch=None):
+        """make_batch(i): step i's inputs (device tensors whose upload / preparation was queued earlier on a side stream);
+        after_launch(i): queues step i + 1's upload / preparation -- called AFTER step i has been launched, so that the host time
+        of those launches and their execution overlap step i on the GPU."""
+        for i in range(2):                      # untimed: allocations
+            step(make_batch(i))
+            if after_launch:
+                after_launch(i)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(args.steps):
-            step(make_batch(i)).detach().to("cpu", non_blocking=False)       # loss read back every step
+            loss = step(make_batch(i))
+            if after_launch:
+                after_launch(i)
+            loss.detach().to("cpu", non_blocking=False)       # loss read back every step
         e1.record()
         barrier()
         tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -409,15 +417,21 @@ def main_sg4d(args):
             side = torch.cuda.Stream(device=dev)
             bufs = [None, None]
 
+            E_ = resident["rel_points"].shape[0] // S
+
             def stage(slot):
-                """step i + 1's scenes: upload AND crop on the side stream while step i computes on the main stream (the
-                front-end's kernels are small latency-bound grids without shared memory: they co-reside with the MLP kernels)"""
+                """one step's scenes: upload AND crop on the side stream while the previous step computes on the main stream (the
+                front-end's kernels are small latency-bound grids without shared memory: they co-reside with the MLP kernels).
+                Every scene's crops are written straight into its slices of the batch tensors."""
                 with torch.cuda.stream(side):
                     pts_d, msk_d = raw_pts.to(dev, non_blocking=True), raw_msk.to(dev, non_blocking=True)
                     sm = {k: v.to(dev, non_blocking=True) for k, v in small.items()}
-                    scenes = [frontend.prepare_scene(pts_d[k], msk_d[k], args.n_obj, args.points, pr, pairs=args.pairs) for k in range(S)]
-                    b = {"obj_points": torch.cat([sc["obj_points"].permute(0, 2, 1) for sc in scenes]).permute(0, 2, 1),
-                         "rel_points": torch.cat([sc["rel_points"].permute(0, 2, 1) for sc in scenes]).permute(0, 2, 1),
+                    obj_all = torch.empty(S * args.n_obj, args.points, raw_pts.shape[2], dtype=torch.float32, device=dev)
+                    rel_all = torch.empty(S * E_, pr, raw_pts.shape[2] + 1, dtype=torch.float32, device=dev)
+                    for k in range(S):
+                        frontend.prepare_scene(pts_d[k], msk_d[k], args.n_obj, args.points, pr, pairs=args.pairs,
+                                               out_obj=obj_all[k * args.n_obj:(k + 1) * args.n_obj], out_rel=rel_all[k * E_:(k + 1) * E_])
+                    b = {"obj_points": obj_all.permute(0, 2, 1), "rel_points": rel_all.permute(0, 2, 1),
                          "edge_indices": resident["edge_indices"]}
                     b.update(sm)
                     if "edge_scene" in resident:
@@ -435,12 +449,14 @@ def main_sg4d(args):
                 for v in b.values():
                     if torch.is_tensor(v):
                         v.record_stream(main)
-                side.wait_stream(main)              # the slot being refilled was last read by the previous step
-                stage((i + 1) & 1)
                 return b
 
+            def stage_next(i):
+                # slot (i + 1) & 1 was last read by step i - 1, whose loss the host has already read back: nothing to wait for
+                stage((i + 1) & 1)
+
             h2d_scene = raw_pts.numel() * 4 + raw_msk.numel() * 4 + sum(v.numel() * v.element_size() for v in small.values())
-            e2e = timed_e2e(scene_batch, h2d_scene)
+            e2e = timed_e2e(scene_batch, h2d_scene, stage_next)
             e2e["input"] = f"{S} raw scenes of {args.scene_points} points + object masks per step; crops built by the GPU front-end"
             bufs = [None, None]
         if args.e2e_input in ("crops", "both"):

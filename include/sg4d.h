@@ -430,7 +430,7 @@ int sg4d_frontend_edges(int P, int stride, int E, const float *pts, const int32_
 /* out (clouds, n, fout): drawn points [xyz | features | (edges only) 1 / 2 for points of the subject / object instance], xyz
  * centred and scaled to the unit sphere; fout = stride (+ 1 with edges).  list / totals as written by the two calls above
  * (edges == NULL: object clouds).  picked (clouds, n) original point indices (may be NULL); mean (clouds, 3); dist (clouds);
- * scratch: clouds * (ceil(n / 256) * 24 + 4) bytes. */
+ * scratch: clouds * (ceil(n / 256) * 24 + 4 + 4 n) bytes (partial sums, max norms and -- when picked is NULL -- the draws). */
 int sg4d_frontend_sample(int P, int stride, int clouds, int n, const float *pts, const int32_t *masks, const int32_t *list,
                          const int *totals, const int64_t *edges, const float *u, float *out, int32_t *picked, float *mean,
                          float *dist, void *scratch, sg4d_stream_t stream);

@@ -58,3 +58,24 @@ def test_frontend_feeds_the_model(cuda):
     loss = m.training_step(batch)
     loss.backward()
     assert torch.isfinite(loss)
+
+
+def test_frontend_writes_into_batch_slices(cuda):
+    """out_obj / out_rel: two scenes cropped straight into their slices of one batch tensor = the per-scene results"""
+    from sg4d import frontend, synthetic
+    n_obj, P, n, n_rel = 4, 6000, 600, 900
+    E = synthetic.edge_list(n_obj, "ordered").shape[1]
+    obj_all = torch.full((2 * n_obj, n, 6), float("nan"), device=cuda)
+    rel_all = torch.full((2 * E, n_rel, 7), float("nan"), device=cuda)
+    for k in range(2):
+        points, masks = synthetic.make_raw_scene(10 + k, n_obj=n_obj, n_points=P)
+        g = torch.Generator().manual_seed(k)
+        u_obj, u_rel = torch.rand(n_obj, n, generator=g).to(cuda), torch.rand(E, n_rel, generator=g).to(cuda)
+        want = frontend.prepare_scene(points.to(cuda), masks.to(cuda), n_obj, n, n_rel, u_obj=u_obj, u_rel=u_rel)
+        got = frontend.prepare_scene(points.to(cuda), masks.to(cuda), n_obj, n, n_rel, u_obj=u_obj, u_rel=u_rel,
+                                     out_obj=obj_all[k * n_obj:(k + 1) * n_obj], out_rel=rel_all[k * E:(k + 1) * E])
+        assert got["obj_points"].data_ptr() == obj_all[k * n_obj].data_ptr()
+        assert torch.equal(obj_all[k * n_obj:(k + 1) * n_obj], want["obj_points"].permute(0, 2, 1))
+        assert torch.equal(rel_all[k * E:(k + 1) * E], want["rel_points"].permute(0, 2, 1))
+    with pytest.raises(RuntimeError):
+        frontend.prepare_scene(points.to(cuda), masks.to(cuda), n_obj, n, n_rel, out_obj=obj_all[:n_obj, :, :5])
