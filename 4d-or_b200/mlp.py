@@ -12,6 +12,12 @@ features, forward and backward:
             y1, y2 and a handful of per-channel constants computed here -- no dY tensor is ever materialised.
 
 Saved for backward: x, y1, y2 (pre-activations), the pooled selection (value + row index) and per-channel vectors.
+
+``fused_sa_scale`` goes from the ball-query indices to the pooled features without the grouped tensor (include/sg4d.h
+section 4): ``_FusedSA1`` recomputes the K <= 7 first layer inside the operand stagers and forms its second-layer weight
+gradient from the Gram matrix of the recomputed activations; ``_FusedSA2`` uses the first layer's linearity -- one small GEMM
+per SOURCE POINT, the grouped activations are a gather ``Z[idx] - Cc[centre]``, and the backward pass reduces dY1 per source
+point / per centre before three small GEMMs.
 """
 import torch
 import torch.nn as nn
