@@ -433,17 +433,24 @@ gather_y1_kernel(long long rows, int n, int m, int nsample, int c1, const float 
                  const int32_t *__restrict__ idx, float *__restrict__ y1, double *__restrict__ partial) {
     const int vec = c1 >> 2, lanes = 256 / vec;
     const int cg = threadIdx.x % vec, rl = threadIdx.x / vec;
-    const long long per_cloud = (long long)m * nsample;
     float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
     double ds[4] = {0.0, 0.0, 0.0, 0.0}, dq[4] = {0.0, 0.0, 0.0, 0.0};
     int since = 0;
-    for (long long r = (long long)blockIdx.x * lanes + rl; r < rows; r += (long long)gridDim.x * lanes) {
-        const long long cloud = r / per_cloud;
-        const long long g = r / nsample;
-        const float4 z = __ldg(reinterpret_cast<const float4 *>(Z + (cloud * n + __ldg(idx + r)) * c1) + cg);
-        const float4 c = __ldg(reinterpret_cast<const float4 *>(Cc + g * c1) + cg);
+    // (group, cloud) with 32-bit divisions (groups < 2^31, checked by the launcher; a 64-bit division costs ~100 instructions);
+    // the neighbour index of a thread's NEXT row is loaded one iteration ahead of the gather that depends on it
+    const long long stride = (long long)gridDim.x * lanes;
+    long long r = (long long)blockIdx.x * lanes + rl;
+    int ix = r < rows ? __ldg(idx + r) : 0;
+    for (; r < rows; r += stride) {
+        const long long rn = r + stride;
+        const int ixn = rn < rows ? __ldg(idx + rn) : 0;
+        const uint32_t g = rows <= 0xffffffffLL ? (uint32_t)r / (uint32_t)nsample : (uint32_t)(r / nsample);
+        const uint32_t cloud = g / (uint32_t)m;
+        const float4 z = __ldg(reinterpret_cast<const float4 *>(Z + ((size_t)cloud * n + ix) * c1) + cg);
+        const float4 c = __ldg(reinterpret_cast<const float4 *>(Cc + (size_t)g * c1) + cg);
         const float4 y = make_float4(z.x - c.x, z.y - c.y, z.z - c.z, z.w - c.w);
         reinterpret_cast<float4 *>(y1 + r * c1)[cg] = y;
+        ix = ixn;
         s[0] += y.x, s[1] += y.y, s[2] += y.z, s[3] += y.w;
         q[0] = fmaf(y.x, y.x, q[0]), q[1] = fmaf(y.y, y.y, q[1]), q[2] = fmaf(y.z, y.z, q[2]), q[3] = fmaf(y.w, y.w, q[3]);
         if (++since == 64) {   // fp32 over short runs, fp64 across them
@@ -507,7 +514,8 @@ extern "C" int sg4d_gather_y1_parts(int c1) { return SG4D_NUM_SMS * 8 * c1; }   
 
 extern "C" int sg4d_gather_y1(long long rows, int n, int m, int nsample, int c1, const float *z, const float *cc,
                               const int32_t *idx, float *y1, double *partial, sg4d_stream_t stream) {
-    if (rows <= 0 || n <= 0 || m <= 0 || nsample <= 0 || (c1 != 64 && c1 != 128) || rows % ((long long)m * nsample) || !z || !cc ||
+    if (rows <= 0 || n <= 0 || m <= 0 || nsample <= 0 || (c1 != 64 && c1 != 128) || rows % ((long long)m * nsample) ||
+        rows / nsample > 0x7fffffffLL || !z || !cc ||
         !idx || !y1 || !partial || ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(cc) | reinterpret_cast<uintptr_t>(y1)) & 15))
         return SG4D_EINVAL;
     gather_y1_kernel<<<SG4D_NUM_SMS * 8, 256, 0, (cudaStream_t)stream>>>(rows, n, m, nsample, c1, z, cc, idx, y1, partial);
