@@ -183,3 +183,24 @@ def test_loss_scaler_follows_grad_scaler_rule():
         w.grad = torch.ones(2)
         sc.step(opt)
     assert sc.scale_value == 8.0
+
+
+def test_fused_scale_dispatch():
+    """which fused kernel family a set-abstraction scale runs on (host logic of sg4d.mlp.sa_scale_kind): the model's SA1 scales
+    recompute their first layer, its SA2 scales go through the first layer's linearity, anything else materialises rows"""
+    from sg4d import mlp
+    from sg4d.pointnet2_ops.pointnet2_modules import build_shared_mlp
+    sa1 = build_shared_mlp([3 + 3, 64, 64])
+    sa1b = build_shared_mlp([3 + 4, 64, 128])
+    sa2 = build_shared_mlp([3 + 192, 128, 128])
+    assert mlp.sa_scale_kind(sa1, 3, 16, False, 6, 3) == "sa1"
+    assert mlp.sa_scale_kind(sa1b, 4, 32, False, 7, 3) == "sa1"
+    assert mlp.sa_scale_kind(sa2, 192, 64, True, 192, 0) == "sa2"
+    assert mlp.sa_scale_kind(sa2, 192, 64, False, 192, 0) == "sa2"            # no feature gradient needed: same kernels, no dFeats
+    assert mlp.sa_scale_kind(build_shared_mlp([3 + 36, 64, 128]), 36, 32, True, 36, 0) == "sa2"
+    assert mlp.sa_scale_kind(build_shared_mlp([3 + 4, 64, 128]), 4, 32, True, 4, 0) == "sa2"   # gradient into 4 features
+    assert mlp.sa_scale_kind(build_shared_mlp([3 + 5, 64, 128]), 5, 32, True, 5, 0) is None    # 5 features: not a multiple of 4
+    assert mlp.sa_scale_kind(sa2, 192, 48, True, 192, 0) is None              # nsample must be a power of two in 8..128
+    assert mlp.sa_scale_kind(build_shared_mlp([3 + 192, 128, 256]), 192, 64, True, 192, 0) is None   # pooled width > 128
+    assert mlp.sa_scale_kind(build_shared_mlp([3 + 192, 128, 64]), 192, 128, True, 192, 0) is None   # 64-wide pool: groups <= 64
+    assert mlp.sa_scale_kind(build_shared_mlp([3 + 192, 128, 128, 128]), 192, 64, True, 192, 0) is None  # three layers
