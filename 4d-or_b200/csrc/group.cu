@@ -438,22 +438,34 @@ gather_y1_kernel(long long rows, int n, int m, int nsample, int c1, const float 
     int since = 0;
     // (group, cloud) with 32-bit divisions (groups < 2^31, checked by the launcher; a 64-bit division costs ~100 instructions);
     // the neighbour index of a thread's NEXT row is loaded one iteration ahead of the gather that depends on it
+    // two rows per thread and iteration (r and r + stride): twice the bytes in flight per warp
     const long long stride = (long long)gridDim.x * lanes;
     long long r = (long long)blockIdx.x * lanes + rl;
-    int ix = r < rows ? __ldg(idx + r) : 0;
-    for (; r < rows; r += stride) {
-        const long long rn = r + stride;
-        const int ixn = rn < rows ? __ldg(idx + rn) : 0;
-        const uint32_t g = rows <= 0xffffffffLL ? (uint32_t)r / (uint32_t)nsample : (uint32_t)(r / nsample);
-        const uint32_t cloud = g / (uint32_t)m;
-        const float4 z = __ldg(reinterpret_cast<const float4 *>(Z + ((size_t)cloud * n + ix) * c1) + cg);
-        const float4 c = __ldg(reinterpret_cast<const float4 *>(Cc + (size_t)g * c1) + cg);
-        const float4 y = make_float4(z.x - c.x, z.y - c.y, z.z - c.z, z.w - c.w);
+    int ix0 = r < rows ? __ldg(idx + r) : 0, ix1 = r + stride < rows ? __ldg(idx + r + stride) : 0;
+    const bool small = rows <= 0xffffffffLL;
+    for (; r < rows; r += 2 * stride) {
+        const long long r1 = r + stride, rn0 = r + 2 * stride, rn1 = r + 3 * stride;
+        const bool two = r1 < rows;
+        const int ixn0 = rn0 < rows ? __ldg(idx + rn0) : 0, ixn1 = rn1 < rows ? __ldg(idx + rn1) : 0;
+        const uint32_t g0 = small ? (uint32_t)r / (uint32_t)nsample : (uint32_t)(r / nsample);
+        const uint32_t g1 = two ? (small ? (uint32_t)r1 / (uint32_t)nsample : (uint32_t)(r1 / nsample)) : g0;
+        const uint32_t cl0 = g0 / (uint32_t)m, cl1 = g1 / (uint32_t)m;
+        const float4 z0 = __ldg(reinterpret_cast<const float4 *>(Z + ((size_t)cl0 * n + ix0) * c1) + cg);
+        const float4 z1 = __ldg(reinterpret_cast<const float4 *>(Z + ((size_t)cl1 * n + ix1) * c1) + cg);
+        const float4 c0 = __ldg(reinterpret_cast<const float4 *>(Cc + (size_t)g0 * c1) + cg);
+        const float4 cc1 = __ldg(reinterpret_cast<const float4 *>(Cc + (size_t)g1 * c1) + cg);
+        const float4 y = make_float4(z0.x - c0.x, z0.y - c0.y, z0.z - c0.z, z0.w - c0.w);
         reinterpret_cast<float4 *>(y1 + r * c1)[cg] = y;
-        ix = ixn;
         s[0] += y.x, s[1] += y.y, s[2] += y.z, s[3] += y.w;
         q[0] = fmaf(y.x, y.x, q[0]), q[1] = fmaf(y.y, y.y, q[1]), q[2] = fmaf(y.z, y.z, q[2]), q[3] = fmaf(y.w, y.w, q[3]);
-        if (++since == 64) {   // fp32 over short runs, fp64 across them
+        if (two) {
+            const float4 w = make_float4(z1.x - cc1.x, z1.y - cc1.y, z1.z - cc1.z, z1.w - cc1.w);
+            reinterpret_cast<float4 *>(y1 + r1 * c1)[cg] = w;
+            s[0] += w.x, s[1] += w.y, s[2] += w.z, s[3] += w.w;
+            q[0] = fmaf(w.x, w.x, q[0]), q[1] = fmaf(w.y, w.y, q[1]), q[2] = fmaf(w.z, w.z, q[2]), q[3] = fmaf(w.w, w.w, q[3]);
+        }
+        ix0 = ixn0, ix1 = ixn1;
+        if (++since == 32) {   // fp32 over short runs (64 rows), fp64 across them
 #pragma unroll
             for (int u = 0; u < 4; ++u) ds[u] += (double)s[u], dq[u] += (double)q[u], s[u] = 0.f, q[u] = 0.f;
             since = 0;
