@@ -244,6 +244,26 @@ group_rows_grad_kernel(int n, int m, int nsample, int c, int out_stride, int gco
                 const int jj = j0 + l;
                 const int pp = __shfl_sync(0xffffffffu, pos, l);
                 const int cc = __shfl_sync(0xffffffffu, cj, l);
+                if (DY && pp != 0 && mask) {
+                    // two plain matches (one row each) per trip: four loads in flight, added in the same order as one by one
+                    const int l2 = __ffs(mask) - 1;
+                    const int pp2 = __shfl_sync(0xffffffffu, pos, l2);
+                    if (pp2 != 0) {
+                        mask &= mask - 1;
+                        if (lane < c4) {
+                            const size_t ra = ((size_t)jj * nsample + pp) * out_stride, rb = ((size_t)(j0 + l2) * nsample + pp2) * out_stride;
+                            const float4 dza = __ldg(reinterpret_cast<const float4 *>(grad_out + ra + gcol0) + lane);
+                            const float4 ya = __ldg(reinterpret_cast<const float4 *>(y1 + ra) + lane);
+                            const float4 dzb = __ldg(reinterpret_cast<const float4 *>(grad_out + rb + gcol0) + lane);
+                            const float4 yb = __ldg(reinterpret_cast<const float4 *>(y1 + rb) + lane);
+                            acc[0] += fmaf(dza.x, pv.x, -fmaf(ya.x, qv.x, uv.x)), acc[1] += fmaf(dza.y, pv.y, -fmaf(ya.y, qv.y, uv.y));
+                            acc[2] += fmaf(dza.z, pv.z, -fmaf(ya.z, qv.z, uv.z)), acc[3] += fmaf(dza.w, pv.w, -fmaf(ya.w, qv.w, uv.w));
+                            acc[0] += fmaf(dzb.x, pv.x, -fmaf(yb.x, qv.x, uv.x)), acc[1] += fmaf(dzb.y, pv.y, -fmaf(yb.y, qv.y, uv.y));
+                            acc[2] += fmaf(dzb.z, pv.z, -fmaf(yb.z, qv.z, uv.z)), acc[3] += fmaf(dzb.w, pv.w, -fmaf(yb.w, qv.w, uv.w));
+                        }
+                        continue;
+                    }
+                }
                 const float *g = grad_out + ((size_t)jj * nsample) * out_stride + gcol0;
                 // slot pp, then (when i is the first hit) the padding slots cc..nsample-1
                 int k = pp;
